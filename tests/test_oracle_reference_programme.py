@@ -1,0 +1,212 @@
+"""Pins the ORACLE (oracle/) by re-running the reference's own test programme against it, with __float128
+finite differences in place of BigFloat, plus the two known-answer anchors that exist for this path.
+
+Reference tests mirrored (paths under the reference tree):
+  examples/ttv_example.ipynb (last cell)     -> test_notebook_known_answer
+  test/test_findtransit.jl:1-24              -> test_findtransit_known_answer
+  test/test_integrator.jl:2-186              -> test_integrator_*
+  test/test_kepler_driftij_gamma.jl:4-286    -> test_kepler_driftij_gamma
+  test/test_phisalpha.jl, test_phic.jl, test_kickfast.jl -> test_kick_pieces
+  test/test_transit_timing.jl:3-97           -> test_transit_timing_*
+  test/test_transit_parameters.jl:3-87       -> test_transit_parameters
+"""
+import numpy as np
+import pytest
+
+from conftest import isapprox_maxabs, tilt
+
+T0 = 7257.93115525
+
+
+def _state3(oracle, elements, mass_scale=100.0, t0=T0):
+    el = elements[:3].copy()
+    el[1, 0] *= mass_scale
+    el[2, 0] *= mass_scale
+    el[:, 6] = 0.0
+    x, v, jac_init = oracle.init_nbody(el, t0)
+    return el, x, v, jac_init
+
+
+def test_notebook_known_answer(oracle):
+    # examples/ttv_example.ipynb: mean interval of body 2's first 8/22/43 transits; printed to 17 digits.
+    el = np.array([[0.82, 0, 0, 0, 0, 0, 0], [3.18e-4, 221.717, 0, 0.0069, 0, np.pi / 2, 0],
+                   [3e-6, 228.774, -228.774 / 6, 0.0054, 0, np.pi / 2, 0]])
+    x, v, jac = oracle.init_nbody(el, 0.0)
+    # printed s.x (6 significant figures), Julia prints x[dim, body]
+    ref_x = np.array([[-2.16714e-6, -2.16714e-6, 0.592581], [1.60063e-20, -4.1079e-17, -2.06854e-17], [0.000261403, -0.670871, -0.337818]])
+    assert np.allclose(x.T, ref_x, rtol=2e-6, atol=0)
+    s = oracle.new_state(x, v, el[:, 0], 0.0)
+    tmax = 9837.282
+    r = oracle.transit_timing(s, 1.0, tmax, oracle.ntt(tmax, el[:, 1]), grad=True, jac_init=jac)
+    t1 = r["tt"][1, : r["count"][1]]
+    got = [np.mean(t1[1:k] - t1[: k - 1]) for k in (8, 22, 43)]
+    ref = [221.80266718923252, 221.78389784838888, 221.78392439692522]
+    assert np.max(np.abs(np.array(got) - np.array(ref))) < 1e-12  # observed 6e-14
+
+
+def test_findtransit_known_answer(oracle, elements):
+    n = 7
+    el = elements[:n]
+    x, v, _ = oracle.init_nbody(el, 7257.0)
+    s = oracle.new_state(x, v, el[:, 0], 7257.0)
+    r = oracle.transit_timing(s, 0.01, 10.0, oracle.ntt(10.0, el[:, 1]), grad=False)
+    for i in range(1, n):
+        assert abs((el[i, 2] - r["tt"][i, 0]) / el[i, 2]) < 1e-6
+
+
+def test_integrator_jacobian_vs_float128_fd(oracle, elements):
+    el, x, v, _ = _state3(oracle, elements)
+    x, v = tilt(x, v)
+    h, nstep = 0.05, 100
+    s = oracle.new_state(x, v, el[:, 0], T0)
+    oracle.integrate(s, h, time=T0 + nstep * h, grad=True)
+    jac_num, _ = oracle.fd_map("ahl21", x, v, el[:, 0], h, nsteps=nstep, dlnq=1e-20, want_dqdt=False)
+    jac = s["jac_step_cm"].T
+    assert isapprox_maxabs(np.arcsinh(jac), np.arcsinh(jac_num))
+    # dqdt after one step (test_integrator.jl:148-175) from the un-tilted state
+    el, x, v, _ = _state3(oracle, elements)
+    s1 = oracle.new_state(x, v, el[:, 0], T0)
+    oracle.integrate(s1, h, nsteps=1, grad=True)
+    _, dq_num = oracle.fd_map("ahl21", x, v, el[:, 0], h, nsteps=1, dlnq=1e-20, want_jac=False)
+    assert isapprox_maxabs(s1["dqdt"], dq_num)
+
+
+def test_integrator_grad_equals_nograd_exactly(oracle, elements):
+    # test_integrator.jl:177-185: x, v identical after 2000 d (40 000 steps) with and without derivatives
+    el, x, v, _ = _state3(oracle, elements)
+    sg = oracle.new_state(x, v, el[:, 0], T0)
+    sn = oracle.new_state(x, v, el[:, 0], T0)
+    oracle.integrate(sn, 0.05, time=T0 + 2000.0, grad=False)
+    oracle.integrate(sg, 0.05, time=T0 + 2000.0, grad=True)
+    assert np.array_equal(sn["x"], sg["x"]) and np.array_equal(sn["v"], sg["v"])
+
+
+@pytest.mark.parametrize("drift_first", [True, False])
+@pytest.mark.parametrize("hyperbolic", [False, True])
+def test_kepler_driftij_gamma(oracle, elements, drift_first, hyperbolic):
+    el = elements[:3].copy()
+    x, v, _ = oracle.init_nbody(el, T0)
+    m = el[:, 0].copy()
+    if hyperbolic:
+        m *= 1e-3
+    x[0, 1] = 5e-1 * np.sqrt(x[0, 0] ** 2 + x[0, 2] ** 2)
+    x[1, 1] = -5e-1 * np.sqrt(x[1, 0] ** 2 + x[1, 2] ** 2)
+    v[0, 1] = 5e-1 * np.sqrt(v[0, 0] ** 2 + v[0, 2] ** 2)
+    v[1, 1] = -5e-1 * np.sqrt(v[1, 0] ** 2 + v[1, 2] ** 2)
+    h = 0.25
+    x1, v1, _, _ = oracle.kepler_driftij(x, v, m, 0, 1, h, drift_first)  # first application (as the reference test does)
+    _, _, jac_ij, dqdt_ij = oracle.kepler_driftij(x1, v1, m, 0, 1, h, drift_first)
+    jac_num, dq_num = oracle.fd_map("kepler_driftij", x1, v1, m, h, i=0, j=1, drift_first=drift_first, dlnq=1e-15)
+    sub = jac_num[:14, :14]
+    assert isapprox_maxabs(jac_ij + np.eye(14), sub)
+    assert isapprox_maxabs(dqdt_ij, dq_num[:14])
+    # grad and no-grad agree exactly on x, v
+    xa, va, _, _ = oracle.kepler_driftij(x1, v1, m, 0, 1, h, drift_first, grad=True)
+    xb, vb, _, _ = oracle.kepler_driftij(x1, v1, m, 0, 1, h, drift_first, grad=False)
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb)
+
+
+@pytest.mark.parametrize("which", ["phisalpha", "phic", "kickfast"])
+def test_kick_pieces(oracle, elements, which):
+    el = elements[:3].copy()
+    n = 3
+    pair = np.zeros((n, n), dtype=bool)
+    if which != "phisalpha":
+        el[1, 0] = 1.0
+        el[2, 0] = 1.0
+        pair[:] = True
+        pair[0, 1:] = False
+        pair[1:, 0] = False
+    x, v, _ = oracle.init_nbody(el, T0)
+    x, v = tilt(x, v)
+    m = el[:, 0].copy()
+    h = 0.05
+    s = oracle.new_state(x, v, m, T0)
+    s["pair"] = pair
+    oracle.integrate(s, h, nsteps=1, grad=False)  # "Take a step"
+    x0, v0 = s["x"].copy(), s["v"].copy()
+    _, _, jac, dq = oracle.kick_piece(which, x0, v0, m, pair, h)
+    jac_num, dq_num = oracle.fd_map(which, x0, v0, m, h, pair=pair, dlnq=1e-15)
+    M = 7 * n
+    assert isapprox_maxabs(jac + np.eye(M), jac_num)
+    # kickfast!: dqdt_kick is d(dv)/dh; phic!/phisalpha!: dqdt_phi likewise
+    assert isapprox_maxabs(dq, dq_num)
+    xa, va, _, _ = oracle.kick_piece(which, x0, v0, m, pair, h, grad=True)
+    xb, vb, _, _ = oracle.kick_piece(which, x0, v0, m, pair, h, grad=False)
+    assert np.array_equal(va, vb)
+
+
+def _tt_setup(elements):
+    N = 3
+    t0 = T0 - 7300.0 - 0.5
+    el = elements[:N].copy()
+    el[1:, 2] -= 7300.0
+    el[:, 6] = 0.0
+    el[1, 0] *= 10.0
+    el[2, 0] *= 10.0
+    return N, t0, el
+
+
+def _mask(N, occs, count, ti, shape):
+    mask = np.zeros(shape, dtype=bool)
+    for jq in range(N):
+        for iq in range(7):
+            for i in occs:
+                for k in range(count[i]):
+                    if iq != 4 and iq != 5 and not (jq == 0 and iq < 6) and not (jq == i and iq == 6):
+                        mask[i, k, iq, jq] = True
+    return mask
+
+
+@pytest.mark.parametrize("ti", [0, pytest.param(1, marks=pytest.mark.slow), pytest.param(2, marks=pytest.mark.slow)])
+def test_transit_timing_dtdelements_vs_float128_fd(oracle, elements, ti):
+    N, t0, el = _tt_setup(elements)
+    h, tmax = 0.04, 10.0
+    x, v, jac_init = oracle.init_nbody(el, t0)
+    ntt = oracle.ntt(tmax, el[:, 1])
+    s = oracle.new_state(x, v, el[:, 0], t0)
+    r = oracle.transit_timing(s, h, tmax, ntt, ti=ti, grad=True, jac_init=jac_init)
+    num, cnt = oracle.fd_transit_elements(el, t0, h, tmax, ntt, ti=ti, dq0=1e-10)
+    assert np.array_equal(cnt, r["count"])
+    assert r["count"].sum() > 0
+    occs = [i for i in range(N) if i != ti]
+    mask = _mask(N, occs, r["count"], ti, r["dtdelements"].shape)
+    assert isapprox_maxabs(np.arcsinh(r["dtdelements"][mask]), np.arcsinh(num[mask]))
+    assert isapprox_maxabs(np.arcsinh(r["dtdelements"]), np.arcsinh(num))
+
+
+def test_transit_timing_grad_equals_nograd_exactly(oracle, elements):
+    # test_transit_timing.jl:91-97 over 2000 d
+    N, t0, el = _tt_setup(elements)
+    x, v, jac_init = oracle.init_nbody(el, t0)
+    tmax = 2000.0
+    ntt = oracle.ntt(tmax, el[:, 1])
+    sg = oracle.new_state(x, v, el[:, 0], t0)
+    sn = oracle.new_state(x, v, el[:, 0], t0)
+    rn = oracle.transit_timing(sn, 0.04, tmax, ntt, grad=False)
+    rg = oracle.transit_timing(sg, 0.04, tmax, ntt, grad=True, jac_init=jac_init)
+    assert rg["count"].sum() > 1000
+    assert np.array_equal(rn["tt"], rg["tt"])
+
+
+def test_transit_parameters_vs_float128_fd(oracle, elements):
+    # test_transit_parameters.jl: (t, vsky, bsky2) and their element derivatives
+    N, t0, el = _tt_setup(elements)
+    h, tmax = 0.04, 10.0
+    x, v, jac_init = oracle.init_nbody(el, t0)
+    ntt = oracle.ntt(tmax, el[:, 1])
+    s = oracle.new_state(x, v, el[:, 0], t0)
+    r = oracle.transit_timing(s, h, tmax, ntt, ti=0, grad=True, jac_init=jac_init, ntbv=3)
+    num, cnt = oracle.fd_transit_elements(el, t0, h, tmax, ntt, ti=0, dq0=1e-10, ntbv=3)
+    assert np.array_equal(cnt, r["count"])
+    # the time row equals TransitTiming's
+    s2 = oracle.new_state(x, v, el[:, 0], t0)
+    r1 = oracle.transit_timing(s2, h, tmax, ntt, ti=0, grad=True, jac_init=jac_init, ntbv=1)
+    assert np.array_equal(r["tt"][0], r1["tt"])
+    assert np.array_equal(r["dtdelements"][0], r1["dtdelements"])
+    mask = _mask(N, [1, 2], r["count"], 0, r["dtdelements"].shape[1:])
+    # as in the reference, the three components are compared in ONE max-norm (b_sky^2 is ~0 for this edge-on system)
+    assert isapprox_maxabs(np.arcsinh(r["dtdelements"][:, mask]), np.arcsinh(num[:, mask]))
+    assert isapprox_maxabs(np.arcsinh(r["dtdelements"]), np.arcsinh(num))
+    # v_sky row on its own is well conditioned
+    assert isapprox_maxabs(np.arcsinh(r["dtdelements"][1][mask]), np.arcsinh(num[1][mask]))
