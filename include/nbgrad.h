@@ -1,0 +1,123 @@
+/* nbgrad.h — C ABI of libnbgrad_b200.so: batched AHL21 step + forward-mode Jacobian + transit timing on B200 (sm_100a).
+ *
+ * The reference (ericagol/NbodyGradient.jl, pure Julia) has no FFI of its own; its only seam is the
+ * Function-valued field Integrator.scheme called once per system per step
+ * (src/integrator/Integrator.jl:17-22,178-180; src/transits/Transits.jl:156-158).  That granularity cannot
+ * cross PCIe, so this ABI sits one level up and replaces the callable-Integrator drivers for a BATCH of
+ * independent systems (batch of 1 = the reference call):
+ *
+ *   nbg_integrate        <-> (intr::Integrator)(s, time; grad) / (s, N; grad) / (s; grad)
+ *                            src/integrator/Integrator.jl:159-197, :211-234, :247
+ *   nbg_transit_timing   <-> (intr::Integrator)(s, tt::TransitTiming|TransitParameters; grad)
+ *                            src/transits/Transits.jl:140-180 + detect_transits!/findtransit!/dtbvdq!/
+ *                            calc_dtdelements!  src/transits/timing.jl:3-194
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every function returns 0 on success or a negative NBG_ERR_*;
+ *    nbg_last_error() gives a thread-local message.  Numerical events (iteration caps, non-finite state,
+ *    transit-slot overflow) are reported per system in `status` and results are still written.
+ *  - all floating point data is IEEE double; arrays are Julia's column-major arrays with the SYSTEM index
+ *    slowest:   x[sys][body][3]  (Julia x[dim,body]),  m[sys][body],
+ *               jac_step[sys][col][row]  (Julia jac_step[row,col], M = 7*nbody),  dqdt[sys][M].
+ *    Row/column index of body i (0-based) in jac_step/dqdt: 7*i+{0,1,2} = x, +{3,4,5} = v, +6 = m
+ *    (src/integrator/ahl21/ahl21.jl:19-21).
+ *  - the caller owns every host pointer; the library owns device memory inside the plan and keeps no host
+ *    pointer after a call returns.  Calls on one plan must be serialised by the caller; different plans may be
+ *    used from different threads.  Calls block until results are in the host buffers.
+ *  - s.pair (Integrator.jl:91) must be all-false (the reference default; nothing in src/ sets it): `pair`
+ *    arguments are accepted as NULL or all-zero, anything else returns NBG_ERR_UNSUPPORTED.
+ *  - there is no CPU fallback: without a CUDA device every compute call returns NBG_ERR_NO_DEVICE.
+ */
+#ifndef NBGRAD_H
+#define NBGRAD_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBG_OK 0
+#define NBG_ERR_ARG (-1)
+#define NBG_ERR_NO_DEVICE (-2)
+#define NBG_ERR_CUDA (-3)
+#define NBG_ERR_UNSUPPORTED (-4)
+#define NBG_ERR_NOMEM (-5)
+
+#define NBG_MAX_BODIES 16
+
+/* per-system status bits */
+#define NBG_ST_NONFINITE 1u       /* x, v not finite at the end */
+#define NBG_ST_TRANSIT_ITMAX 2u   /* findtransit! Newton hit its 20-iteration cap (timing.jl:49,70) */
+#define NBG_ST_EVENT_OVERFLOW 4u  /* more transits in one chunk than the event queue holds; some were dropped */
+#define NBG_ST_NTT_OVERFLOW 8u    /* a body had more transits than its ntt capacity (counted, not stored: timing.jl:18-19) */
+
+typedef struct nbg_plan nbg_plan;
+
+int32_t nbg_version(void);
+const char* nbg_last_error(void);
+int32_t nbg_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+
+/* A plan holds device buffers for `nsys` systems of `nbody` bodies on CUDA device `device`.
+ * stream_budget_bytes bounds the operator-stream buffer (0 = default: 1/4 of free device memory). */
+int32_t nbg_plan_create(nbg_plan** plan, int32_t nbody, int64_t nsys, int32_t device, int64_t stream_budget_bytes);
+int32_t nbg_plan_destroy(nbg_plan* plan);
+
+/* ---- resident state (State{T}, Integrator.jl:49-72) ------------------------------------------------------
+ * nbg_set_state uploads x, v, m (required) and optionally xerror, verror, jac_step, jac_error, dqdt
+ * (NULL = the State(ic) defaults: zeros, jac_step = I; Integrator.jl:82-103), and sets s.t = t0 for all systems.
+ * nbg_get_state downloads whatever is non-NULL. */
+int32_t nbg_set_state(nbg_plan* plan, const double* x, const double* v, const double* m, double t0, const double* xerror,
+                      const double* verror, const double* jac_step, const double* jac_error, const double* dqdt);
+int32_t nbg_get_state(nbg_plan* plan, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error,
+                      double* dqdt, double* t, uint32_t* status);
+
+/* ---- plain integration on the resident state -----------------------------------------------------------------
+ * nsteps steps of size h, then (if h_last != 0) one step of size h_last — exactly what (intr)(s,time) does with
+ * nsteps = |round((time-t0)/h)| and h_last = time - (t0 + h*nsteps) (Integrator.jl:159-197).
+ * time_mode 0: s.t += Kahan sum of h per step ((intr)(s,N), Integrator.jl:229); 1: s.t = t_final. */
+int32_t nbg_integrate_resident(nbg_plan* plan, double h, int64_t nsteps, double h_last, int32_t grad, int32_t time_mode, double t_final);
+
+/* One-shot form with HOST buffers: set_state + integrate + get_state. */
+int32_t nbg_integrate(nbg_plan* plan, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0, double h,
+                      int64_t nsteps, double h_last, int32_t grad, double* x, double* v, double* xerror, double* verror,
+                      double* jac_step, double* jac_error, double* dqdt, uint32_t* status);
+
+/* ---- transit timing ---------------------------------------------------------------------------------------------
+ * Runs nsteps = |round(tmax/h)| steps from the resident state with transit detection for every body except `ti`
+ * (0-based; the reference default ti=1 is 0 here) and Newton refinement of each transit (timing.jl:3-110).
+ *
+ * Output layout ("ragged by body"): body i owns ntt_body[i] slots; off[i] = sum_{b<i} ntt_body[b], RT = sum ntt_body.
+ *   tt[sys][off[i]+k]             k-th transit time of body i            (Julia tt.tt[i,k])
+ *   count[sys][i]                 number of transits detected (may exceed ntt_body[i]; extra ones are not stored)
+ *   dtdq0[sys][off[i]+k][7*p+q]   d tt / d (q-th coordinate of body p)   (Julia tt.dtdq0[i,k,q,p])
+ *   dtdelements[...] same shape    dtdq0 . jac_init                       (Julia tt.dtdelements[i,k,l,k'])
+ * With ntt_body[i] = ntt for all i this is the reference's dense TransitTiming with a permuted index order; unfilled
+ * slots are 0 (Transits.jl:46-48).  jac_init is [sys][col][row] (Julia column-major), NULL = skip dtdelements.
+ * mode 0 = TransitTiming; mode 1 = TransitParameters: tt/dtdq0/dtdelements get a leading component axis of 3
+ * (time, v_sky, b_sky^2): ttbv[sys][off[i]+k][3], dtbvdq0[sys][off[i]+k][7*p+q][3].
+ * grad = 0: times only (dtdq0/dtdelements untouched, no Jacobian propagated).
+ * The *_resident form leaves outputs on the device (nbg_transit_fetch copies them out); the one-shot form uses host
+ * buffers for everything. */
+int32_t nbg_transit_timing_resident(nbg_plan* plan, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode,
+                                    int32_t grad, const double* jac_init_host_or_null);
+int32_t nbg_transit_fetch(nbg_plan* plan, double* tt, int64_t* count, double* dtdq0, double* dtdelements);
+int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0,
+                           double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad,
+                           const double* jac_init, double* tt, int64_t* count, double* dtdq0, double* dtdelements, double* x,
+                           double* v, double* xerror, double* verror, double* jac_step, double* jac_error, double* dqdt,
+                           double* t, uint32_t* status);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------------------
+ * Counters accumulated since plan creation / nbg_counters_reset:
+ *  c[0] main-loop system-steps, c[1] findtransit Newton step-equivalents, c[2] final (Jacobian) transit steps,
+ *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main + transit).
+ * nbg_last_timings: device milliseconds (CUDA events on the plan's stream) spent in the last compute call in the
+ *  trajectory kernel [0], transit-refinement kernel [1], Jacobian kernel [2], everything else [3]; [4] = total. */
+int32_t nbg_counters(nbg_plan* plan, int64_t* c8);
+int32_t nbg_counters_reset(nbg_plan* plan);
+int32_t nbg_last_timings(nbg_plan* plan, double* ms5);
+int64_t nbg_cuda_stream(nbg_plan* plan); /* cudaStream_t of the plan, for callers that time with their own events */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,855 @@
+// libnbgrad_b200.so — kernels and C ABI (include/nbgrad.h).  sm_100a only; no CPU fallback.
+//
+// Pipeline per chunk of S steps (all on the plan's stream):
+//   traj_kernel      one THREAD per system: x, v (Kahan), dq/dh; writes the per-step operator stream, detects
+//                    transits (detect_transits!, timing.jl:3-29) and queues them with a snapshot of the state
+//   transit_kernel   one THREAD per queued transit: findtransit! Newton iterations (timing.jl:31-73), Jacobian-free
+//                    because x, v, dqdt never read jac_step; then the one final step (timing.jl:75-80) whose operator
+//                    stream is written for the Jacobian kernel
+//   jac_kernel       one thread per COLUMN of jac_step, matrix resident in shared memory for the chunk: applies the
+//                    operator stream; at each queued transit saves the matrix, applies the transit step, emits
+//                    dtbvdq! (timing.jl:155-194), restores
+// Data layout in HBM: trajectory state and operator stream are SoA with the system index fastest (lanes = systems,
+// coalesced); jac_step/jac_error are [sys][row 6N][col 7N] (column threads coalesce).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nbgrad.h"
+#include "nbg_jacobian.cuh"
+
+using namespace nbg;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(NBG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct TrajArrays {
+  double *x, *v, *xe, *ve, *m, *dq, *gsave, *t;
+  int32_t* count;
+  uint32_t* status;
+  size_t ld;  // padded system count (leading dimension of every SoA array)
+};
+
+struct EventQueue {
+  int32_t* n;  // number queued this chunk (may exceed cap: overflow)
+  int32_t cap;
+  int32_t *sys, *step, *body, *k;
+  double *dt0, *t;   // initial guess / time of the prior state
+  double* snap;      // [12N][cap]  x, v, xe, ve
+  double* hdr;       // [8][cap]    dx, dy, dvx, dvy, gdot, vsky, dvdt, dt0_final  (written by transit_kernel)
+  double* stream;    // [step_fields][cap] operator stream of the final step
+};
+
+struct TransitOut {
+  double* tt;      // [sys][RT][C]
+  double* dtdq0;   // [sys][RT][M][C]
+  const int32_t* ntt_body;  // device [N]
+  const int32_t* off;       // device [N]
+  int32_t RT, C;            // C = 1 (TransitTiming) or 3 (TransitParameters)
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+template <bool GRAD, bool EMIT>
+__global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, int detect, int ti,
+                                                   double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
+                                                   int32_t* evlist, int time_mode_kahan, double* tkahan_err) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= nsys) return;
+  const size_t ld = T.ld;
+  Body b;
+  double dq[6 * NMAX];
+  for (int q = 0; q < 3 * n; ++q) {
+    b.x[q] = T.x[q * ld + sys]; b.v[q] = T.v[q * ld + sys]; b.xe[q] = T.xe[q * ld + sys]; b.ve[q] = T.ve[q * ld + sys];
+  }
+  for (int q = 0; q < n; ++q) b.m[q] = T.m[q * ld + sys];
+  for (int q = 0; q < 6 * n; ++q) dq[q] = GRAD ? T.dq[q * ld + sys] : 0.0;
+  double gs[NMAX];
+  int32_t cnt[NMAX];
+  if (detect) for (int i = 0; i < n; ++i) { gs[i] = T.gsave[i * ld + sys]; cnt[i] = T.count[i * ld + sys]; }
+  double tnow = T.t[sys], terr = tkahan_err ? tkahan_err[sys] : 0.0;
+  uint32_t st = 0;
+  const size_t sf = step_fields(n);
+  for (int s = 0; s < nsteps; ++s) {
+    Emit em{EMIT ? stream + (size_t)s * sf * ld : nullptr, ld, (size_t)sys};
+    ahl21_step<GRAD, EMIT>(b, dq, n, h, em);
+    if (time_mode_kahan) ksum(tnow, terr, h);                      // (intr)(s,N): Integrator.jl:229
+    else tnow = t0 + ((double)(istep0 + s + 1) * h);               // Transits.jl:161
+    if (detect) {
+      for (int i = 0; i < n; ++i) {
+        int32_t slot = -1;
+        if (i != ti) {
+          const double gi = gsky(b, i, ti);
+          const double ri = sqrt(b.x[3 * i] * b.x[3 * i] + b.x[3 * i + 1] * b.x[3 * i + 1] + b.x[3 * i + 2] * b.x[3 * i + 2]);
+          if (gi > 0.0 && gs[i] < 0.0 && -b.x[3 * i + 2] > 0.25 * ri && ri < 1e12) {
+            cnt[i] += 1;
+            if (cnt[i] <= ntt_body[i]) {
+              slot = atomicAdd(Q.n, 1);
+              if (slot < Q.cap) {
+                Q.sys[slot] = (int32_t)sys; Q.step[slot] = s; Q.body[slot] = i; Q.k[slot] = cnt[i] - 1;
+                Q.dt0[slot] = -gi * h_intr / (gi - gs[i]);
+                Q.t[slot] = tnow;
+                for (int q = 0; q < 3 * n; ++q) {
+                  Q.snap[(size_t)(q)*Q.cap + slot] = b.x[q];
+                  Q.snap[(size_t)(3 * n + q) * Q.cap + slot] = b.v[q];
+                  Q.snap[(size_t)(6 * n + q) * Q.cap + slot] = b.xe[q];
+                  Q.snap[(size_t)(9 * n + q) * Q.cap + slot] = b.ve[q];
+                }
+              } else {
+                slot = -1;
+                st |= NBG_ST_EVENT_OVERFLOW;
+              }
+            } else {
+              st |= NBG_ST_NTT_OVERFLOW;
+            }
+          }
+          gs[i] = gi;
+        }
+        if (evlist) evlist[((size_t)s * n + i) * ld + sys] = slot;
+      }
+    }
+  }
+  bool finite = true;
+  for (int q = 0; q < 3 * n; ++q) {
+    T.x[q * ld + sys] = b.x[q]; T.v[q * ld + sys] = b.v[q]; T.xe[q * ld + sys] = b.xe[q]; T.ve[q * ld + sys] = b.ve[q];
+    finite = finite && isfinite(b.x[q]) && isfinite(b.v[q]);
+  }
+  if (GRAD) for (int q = 0; q < 6 * n; ++q) T.dq[q * ld + sys] = dq[q];
+  if (detect) for (int i = 0; i < n; ++i) { T.gsave[i * ld + sys] = gs[i]; T.count[i * ld + sys] = cnt[i]; }
+  T.t[sys] = tnow;
+  if (tkahan_err) tkahan_err[sys] = terr;
+  if (!finite) st |= NBG_ST_NONFINITE;
+  if (st) atomicOr(&T.status[sys], st);
+}
+
+// initial gsave: Transits.jl:146-149
+__global__ void gsave_init_kernel(TrajArrays T, int n, long nsys, int ti) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= nsys) return;
+  const size_t ld = T.ld;
+  for (int i = 0; i < n; ++i) {
+    double g = 0.0;
+    if (i != ti)
+      g = (T.x[(3 * ti) * ld + sys] - T.x[(3 * i) * ld + sys]) * (T.v[(3 * ti) * ld + sys] - T.v[(3 * i) * ld + sys]) +
+          (T.x[(3 * ti + 1) * ld + sys] - T.x[(3 * i + 1) * ld + sys]) * (T.v[(3 * ti + 1) * ld + sys] - T.v[(3 * i + 1) * ld + sys]);
+    T.gsave[i * ld + sys] = g;
+    T.count[i * ld + sys] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// findtransit! (timing.jl:31-110).  One thread per queued transit.
+template <bool GRAD>
+__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = min(*Q.n, Q.cap);
+  if (e >= nq) return;
+  const int sys = Q.sys[e], j = Q.body[e];
+  const size_t ld = T.ld;
+  Body b0, b;
+  for (int q = 0; q < 3 * n; ++q) {
+    b0.x[q] = Q.snap[(size_t)q * Q.cap + e];
+    b0.v[q] = Q.snap[(size_t)(3 * n + q) * Q.cap + e];
+    b0.xe[q] = Q.snap[(size_t)(6 * n + q) * Q.cap + e];
+    b0.ve[q] = Q.snap[(size_t)(9 * n + q) * Q.cap + e];
+  }
+  for (int q = 0; q < n; ++q) b0.m[q] = T.m[q * ld + sys];
+  double dq[6 * NMAX];
+  double dt0 = Q.dt0[e], stmp = 0.0;
+  double tt1 = dt0 + 1.0, tt2 = dt0 + 2.0;
+  int iter = 0;
+  Emit none{nullptr, 0, 0};
+  while (true) {
+    tt2 = tt1;
+    tt1 = dt0;
+    b = b0;
+    ahl21_step<true, false>(b, dq, n, dt0, none);
+    const double gs = gsky(b, ti, j);
+    const double gd = gdot(b, dq, ti, j);
+    const double dt = -gs / gd;
+    ksum(dt0, stmp, dt);
+    iter += 1;
+    if (iter >= 20 || dt0 == tt1 || dt0 == tt2) break;
+  }
+  uint32_t st = (iter >= 20) ? NBG_ST_TRANSIT_ITMAX : 0u;
+  if (GRAD) {
+    b = b0;
+    Emit em{Q.stream, (size_t)Q.cap, (size_t)e};
+    ahl21_step<true, true>(b, dq, n, dt0, em);
+  }
+  const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
+  const double dvx = b.v[3 * j] - b.v[3 * ti], dvy = b.v[3 * j + 1] - b.v[3 * ti + 1];
+  const double vsky = sqrt(dvx * dvx + dvy * dvy), bsky2 = dx * dx + dy * dy;
+  const size_t rec = (size_t)sys * O.RT + O.off[j] + Q.k[e];
+  O.tt[rec * O.C] = Q.t[e] + dt0;
+  if (O.C == 3) { O.tt[rec * 3 + 1] = vsky; O.tt[rec * 3 + 2] = bsky2; }
+  if (GRAD) {
+    const double gd = gdot(b, dq, ti, j);
+    const double dvdt = (dvx * (dq[6 * j + 3] - dq[6 * ti + 3]) + dvy * (dq[6 * j + 4] - dq[6 * ti + 4])) / vsky;
+    double* H = Q.hdr;
+    const size_t cap = Q.cap;
+    H[0 * cap + e] = dx; H[1 * cap + e] = dy; H[2 * cap + e] = dvx; H[3 * cap + e] = dvy;
+    H[4 * cap + e] = gd; H[5 * cap + e] = vsky; H[6 * cap + e] = dvdt; H[7 * cap + e] = dt0;
+  }
+  if (st) atomicOr(&T.status[sys], st);
+  atomicAdd(&counters[1], (unsigned long long)iter);
+  atomicAdd(&counters[3], 1ull);
+  if (GRAD) atomicAdd(&counters[2], 1ull);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Jacobian kernel: one block per system, blockDim = 32*ceil(M/32) threads, thread c owns column c.
+__global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, int n, size_t ld, const double* stream,
+                           int nsteps, double h, const int32_t* evlist, EventQueue Q, int ti, TransitOut O, int stage_phi) {
+  extern __shared__ double sm[];
+  const int M = 7 * n, R6 = 6 * n, P = npairs(n);
+  const long sys = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, c = tid;
+  JacSmem S;
+  S.Jv = sm;
+  S.Je = S.Jv + (size_t)R6 * M;
+  S.da = S.Je + (size_t)R6 * M;
+  S.rec = S.da + (size_t)3 * n * M;
+  S.phi = stage_phi ? S.rec + 2 * KF : nullptr;
+  (void)P;
+  const size_t jsz = (size_t)R6 * M;
+  for (size_t q = tid; q < jsz; q += nthr) { S.Jv[q] = Jv_g[sys * jsz + q]; S.Je[q] = Je_g[sys * jsz + q]; }
+  __syncthreads();
+  const size_t sf = step_fields(n);
+  for (int s = 0; s < nsteps; ++s) {
+    Src src{stream + (size_t)s * sf * ld, ld, (size_t)sys};
+    jac_apply_step(S, src, n, M, c, 0.5 * h, tid, nthr);
+    if (evlist) {
+      for (int i = 0; i < n; ++i) {
+        const int32_t slot = evlist[((size_t)s * n + i) * ld + sys];
+        if (slot < 0) continue;  // uniform across the block
+        // save the prior matrix (set_state!(s_prior,...)), apply the transit step, emit dtbvdq!, restore
+        __syncthreads();
+        for (size_t q = tid; q < jsz; q += nthr) { Jbak[sys * 2 * jsz + q] = S.Jv[q]; Jbak[sys * 2 * jsz + jsz + q] = S.Je[q]; }
+        __syncthreads();
+        const size_t cap = Q.cap;
+        const double dt0 = Q.hdr[7 * cap + slot];
+        Src ev{Q.stream, cap, (size_t)slot};
+        jac_apply_step(S, ev, n, M, c, 0.5 * dt0, tid, nthr);
+        if (c < M) {
+          const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
+          const double gd = Q.hdr[4 * cap + slot];
+          const int j = i;  // occultor
+          const double jx0 = S.Jv[(6 * j) * M + c] - S.Jv[(6 * ti) * M + c], jx1 = S.Jv[(6 * j + 1) * M + c] - S.Jv[(6 * ti + 1) * M + c];
+          const double jv0 = S.Jv[(6 * j + 3) * M + c] - S.Jv[(6 * ti + 3) * M + c], jv1 = S.Jv[(6 * j + 4) * M + c] - S.Jv[(6 * ti + 4) * M + c];
+          const double dtdq = -(jx0 * dvx + jx1 * dvy + jv0 * dx + jv1 * dy) / gd;
+          const size_t rec = (size_t)sys * O.RT + O.off[j] + Q.k[slot];
+          if (O.C == 1) {
+            O.dtdq0[rec * M + c] = dtdq;
+          } else {
+            const double vsky = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
+            O.dtdq0[(rec * M + c) * 3] = dtdq;
+            O.dtdq0[(rec * M + c) * 3 + 1] = (jv0 * dvx + jv1 * dvy) / vsky + dvdt * dtdq;
+            O.dtdq0[(rec * M + c) * 3 + 2] = 2.0 * (jx0 * dx + jx1 * dy);
+          }
+        }
+        __syncthreads();
+        for (size_t q = tid; q < jsz; q += nthr) { S.Jv[q] = Jbak[sys * 2 * jsz + q]; S.Je[q] = Jbak[sys * 2 * jsz + jsz + q]; }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  for (size_t q = tid; q < jsz; q += nthr) { Jv_g[sys * jsz + q] = S.Jv[q]; Je_g[sys * jsz + q] = S.Je[q]; }
+}
+
+// dtdelements = dtdq0 . jac_init  (calc_dtdelements!, timing.jl:112-138).  One block per (system, record tile).
+__global__ void dtdelements_kernel(const double* __restrict__ dtdq0, const double* __restrict__ jac_init, double* __restrict__ out,
+                                   const int32_t* __restrict__ count, const int32_t* ntt_body, const int32_t* off, int n, size_t ld, int RT, int C) {
+  extern __shared__ double ji[];  // M x M column-major: ji[col*M + row]
+  const int M = 7 * n;
+  const long sys = blockIdx.x;
+  for (int q = threadIdx.x; q < M * M; q += blockDim.x) ji[q] = jac_init[(size_t)sys * M * M + q];
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const int nk = min(count[i * ld + sys], ntt_body[i]);
+    for (int idx = threadIdx.x; idx < nk * M * C; idx += blockDim.x) {
+      const int comp = idx % C, col = (idx / C) % M, k = idx / (C * M);
+      const size_t rec = (size_t)sys * RT + off[i] + k;
+      double acc = 0.0;
+      for (int row = 0; row < M; ++row) acc += dtdq0[(rec * M + row) * C + comp] * ji[col * M + row];
+      out[(rec * M + col) * C + comp] = acc;
+    }
+  }
+}
+
+// ---- layout conversion kernels (host AoS <-> device SoA) ----
+__global__ void pack_xvm_kernel(const double* x, const double* v, const double* m, const double* xe, const double* ve, const double* dqdt,
+                                TrajArrays T, int n, long nsys, double t0) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= nsys) return;
+  const size_t ld = T.ld;
+  for (int q = 0; q < 3 * n; ++q) {
+    T.x[q * ld + sys] = x[sys * 3 * n + q];
+    T.v[q * ld + sys] = v[sys * 3 * n + q];
+    T.xe[q * ld + sys] = xe ? xe[sys * 3 * n + q] : 0.0;
+    T.ve[q * ld + sys] = ve ? ve[sys * 3 * n + q] : 0.0;
+  }
+  for (int q = 0; q < n; ++q) T.m[q * ld + sys] = m[sys * n + q];
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 6; ++k) T.dq[(6 * i + k) * ld + sys] = dqdt ? dqdt[sys * 7 * n + 7 * i + k] : 0.0;
+  T.t[sys] = t0;
+  T.status[sys] = 0;
+}
+__global__ void unpack_xv_kernel(TrajArrays T, int n, long nsys, double* x, double* v, double* xe, double* ve, double* dqdt) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= nsys) return;
+  const size_t ld = T.ld;
+  for (int q = 0; q < 3 * n; ++q) {
+    if (x) x[sys * 3 * n + q] = T.x[q * ld + sys];
+    if (v) v[sys * 3 * n + q] = T.v[q * ld + sys];
+    if (xe) xe[sys * 3 * n + q] = T.xe[q * ld + sys];
+    if (ve) ve[sys * 3 * n + q] = T.ve[q * ld + sys];
+  }
+  if (dqdt)
+    for (int i = 0; i < n; ++i) {
+      for (int k = 0; k < 6; ++k) dqdt[sys * 7 * n + 7 * i + k] = T.dq[(6 * i + k) * ld + sys];
+      dqdt[sys * 7 * n + 7 * i + 6] = 0.0;
+    }
+}
+// device [sys][6N][M] <-> Julia [sys][col][row] (M x M), identity mass rows
+__global__ void jac_to_julia_kernel(const double* J6, double* out, int n, int is_error) {
+  const int M = 7 * n;
+  const long sys = blockIdx.x;
+  for (int q = threadIdx.x; q < M * M; q += blockDim.x) {
+    const int col = q / M, row = q % M, b = row / 7, k = row % 7;
+    double val;
+    if (k == 6) val = (!is_error && row == col) ? 1.0 : 0.0;
+    else val = J6[((size_t)sys * 6 * n + 6 * b + k) * M + col];
+    out[(size_t)sys * M * M + q] = val;
+  }
+}
+__global__ void jac_from_julia_kernel(const double* in, double* J6, int n, int is_error) {
+  const int M = 7 * n;
+  const long sys = blockIdx.x;
+  for (int q = threadIdx.x; q < 6 * n * M; q += blockDim.x) {
+    const int r6 = q / M, col = q % M, b = r6 / 6, k = r6 % 6;
+    double val;
+    if (in) val = in[(size_t)sys * M * M + (size_t)col * M + 7 * b + k];
+    else val = (!is_error && (7 * b + k) == col) ? 1.0 : 0.0;
+    J6[(size_t)sys * 6 * n * M + q] = val;
+  }
+}
+__global__ void count_out_kernel(const int32_t* count, size_t ld, int n, long nsys, int64_t* out) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= nsys) return;
+  for (int i = 0; i < n; ++i) out[sys * n + i] = count[i * ld + sys];
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t b) {
+    if (b <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    if (cudaMalloc(&p, b) != cudaSuccess) { cudaGetLastError(); return -1; }
+    bytes = b;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+struct nbg_plan {
+  int n = 0, device = 0;
+  long nsys = 0;
+  size_t ld = 0;
+  int64_t stream_budget = 0;
+  cudaStream_t stream = nullptr;
+  TrajArrays T{};
+  DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
+  DevBuf bJv, bJe, bJbak, bstream, bevlist;
+  DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
+  DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
+  DevBuf stage[8];  // staging for host<->device conversions
+  bool has_state = false, jac_valid = false;
+  int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
+  int RT = 0, C = 1;
+  bool have_transit = false, have_dtde = false, transit_grad = false;
+  unsigned long long counters_host[8] = {0};
+  double timings[5] = {0, 0, 0, 0, 0};
+  long launches = 0;
+};
+
+namespace {
+
+int alloc_state(nbg_plan* p) {
+  const size_t ld = p->ld, n = p->n;
+  const size_t M = 7 * n;
+  int bad = 0;
+  bad |= p->bx.ensure(3 * n * ld * 8); bad |= p->bv.ensure(3 * n * ld * 8); bad |= p->bxe.ensure(3 * n * ld * 8); bad |= p->bve.ensure(3 * n * ld * 8);
+  bad |= p->bm.ensure(n * ld * 8); bad |= p->bdq.ensure(6 * n * ld * 8); bad |= p->bgs.ensure(n * ld * 8); bad |= p->bt.ensure(ld * 8);
+  bad |= p->bterr.ensure(ld * 8); bad |= p->bcount.ensure(n * ld * 4); bad |= p->bstatus.ensure(ld * 4);
+  bad |= p->bcounters.ensure(8 * 8); bad |= p->bntt.ensure(NBG_MAX_BODIES * 4); bad |= p->boff.ensure(NBG_MAX_BODIES * 4);
+  bad |= p->qn.ensure(4);
+  (void)M;
+  if (bad) return -1;
+  p->T = TrajArrays{p->bx.as<double>(), p->bv.as<double>(), p->bxe.as<double>(), p->bve.as<double>(), p->bm.as<double>(), p->bdq.as<double>(),
+                    p->bgs.as<double>(), p->bt.as<double>(), p->bcount.as<int32_t>(), p->bstatus.as<uint32_t>(), ld};
+  return 0;
+}
+
+size_t jac_smem_bytes(int n, bool stage_phi) {
+  const size_t M = 7 * n, R6 = 6 * n;
+  size_t d = 2 * R6 * M + 3 * (size_t)n * M + 2 * KF + (stage_phi ? (size_t)npairs(n) * PF : 0);
+  return d * 8;
+}
+
+struct Timer {
+  cudaStream_t s;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+  void begin(int kind) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    ev.push_back({kind, {a, b}});
+  }
+  void end() { cudaEventRecord(ev.back().second.second, s); }
+  void collect(double* ms4) {
+    for (auto& e : ev) {
+      float t = 0;
+      cudaEventElapsedTime(&t, e.second.first, e.second.second);
+      ms4[e.first] += t;
+      cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+    }
+    ev.clear();
+  }
+};
+
+double check_step(double t0, double tmax) {  // Integrator.jl:249-259
+  auto sg = [](double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); };
+  if (std::fabs(tmax) > std::fabs(t0)) return sg(tmax);
+  if (sg(tmax) != sg(t0)) return sg(tmax);
+  return -1 * sg(tmax);
+}
+
+// core driver: runs `nsteps` steps of size h from the resident state in chunks.
+// detect: transit detection on; grad: propagate Jacobian; kahan_time: s.t accumulates h with Kahan
+int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti, double t0, double h_intr, bool kahan_time, Timer& tm,
+              double rate_hint) {
+  if (nsteps <= 0) return 0;
+  const int n = p->n;
+  const long nsys = p->nsys;
+  const size_t ld = p->ld;
+  const size_t sf = step_fields(n);
+  const size_t jsz = (size_t)6 * n * 7 * n;
+  // chunk length from the stream budget
+  size_t per_step = sf * ld * 8;
+  long S = 1;
+  if (grad) {
+    S = (long)std::max<int64_t>(1, std::min<int64_t>(p->stream_budget / (int64_t)per_step, 64));
+    S = std::min(S, nsteps);
+    if (p->bstream.ensure((size_t)S * per_step)) return fail(NBG_ERR_NOMEM, "operator stream allocation failed");
+  } else {
+    S = std::min<long>(nsteps, 256);
+  }
+  EventQueue Q{};
+  TransitOut O{};
+  int32_t* evlist = nullptr;
+  if (detect) {
+    double rate = std::min<double>(n - 1, rate_hint * 2.0 + 0.05);
+    long cap = (long)std::ceil((double)nsys * (double)S * rate) + 4096;
+    cap = std::min<long>(cap, (long)nsys * S * (n - 1));
+    cap = std::max<long>(cap, 32);
+    cap = (cap + 31) / 32 * 32;
+    int bad = 0;
+    bad |= p->qsys.ensure(cap * 4); bad |= p->qstep.ensure(cap * 4); bad |= p->qbody.ensure(cap * 4); bad |= p->qk.ensure(cap * 4);
+    bad |= p->qdt0.ensure(cap * 8); bad |= p->qt.ensure(cap * 8); bad |= p->qsnap.ensure((size_t)12 * n * cap * 8);
+    bad |= p->qhdr.ensure((size_t)8 * cap * 8);
+    if (grad) bad |= p->qstream.ensure(sf * (size_t)cap * 8);
+    bad |= p->bevlist.ensure((size_t)S * n * ld * 4);
+    if (bad) return fail(NBG_ERR_NOMEM, "event queue allocation failed");
+    Q = EventQueue{p->qn.as<int32_t>(), (int32_t)cap, p->qsys.as<int32_t>(), p->qstep.as<int32_t>(), p->qbody.as<int32_t>(), p->qk.as<int32_t>(),
+                   p->qdt0.as<double>(), p->qt.as<double>(), p->qsnap.as<double>(), p->qhdr.as<double>(), p->qstream.as<double>()};
+    O = TransitOut{p->btt.as<double>(), p->bdtdq0.as<double>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->RT, p->C};
+    evlist = p->bevlist.as<int32_t>();
+  }
+  if (grad && detect) {
+    if (p->bJbak.ensure((size_t)nsys * 2 * jsz * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
+  }
+  const int tpb = 128;
+  const unsigned gridA = (unsigned)((nsys + tpb - 1) / tpb);
+  const int tps = 32 * ((7 * n + 31) / 32);
+  bool stage_phi = true;
+  size_t smem = jac_smem_bytes(n, true);
+  if (smem > 227 * 1024) { stage_phi = false; smem = jac_smem_bytes(n, false); }
+  if (grad) {
+    if (smem > 227 * 1024) return fail(NBG_ERR_UNSUPPORTED, "jac_step does not fit in shared memory for this nbody");
+    CK(cudaFuncSetAttribute(jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  unsigned long long* dcount = p->bcounters.as<unsigned long long>();
+  long done = 0;
+  while (done < nsteps) {
+    const int s = (int)std::min<long>(S, nsteps - done);
+    if (detect) CK(cudaMemsetAsync(p->qn.p, 0, 4, p->stream));
+    tm.begin(0);
+    double* tkerr = kahan_time ? p->bterr.as<double>() : nullptr;
+    if (grad)
+      traj_kernel<true, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), detect, ti, t0, done, h_intr,
+                                                          p->bntt.as<int32_t>(), Q, evlist, kahan_time, tkerr);
+    else
+      traj_kernel<false, false><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
+                                                            Q, evlist, kahan_time, tkerr);
+    tm.end();
+    p->launches++;
+    if (detect) {
+      tm.begin(1);
+      const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
+      if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount);
+      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount);
+      tm.end();
+      p->launches++;
+    }
+    if (grad) {
+      tm.begin(2);
+      jac_kernel<<<(unsigned)nsys, tps, smem, p->stream>>>(p->bJv.as<double>(), p->bJe.as<double>(), p->bJbak.as<double>(), n, ld,
+                                                          p->bstream.as<double>(), s, h, detect ? evlist : nullptr, Q, ti, O, stage_phi ? 1 : 0);
+      tm.end();
+      p->launches++;
+    }
+    CK(cudaGetLastError());
+    done += s;
+    p->counters_host[0] += (unsigned long long)nsys * s;
+    if (grad) p->counters_host[5] += (unsigned long long)nsys * s;
+  }
+  return 0;
+}
+
+int ensure_jac(nbg_plan* p) {
+  const size_t jsz = (size_t)6 * p->n * 7 * p->n;
+  if (p->bJv.ensure((size_t)p->nsys * jsz * 8) || p->bJe.ensure((size_t)p->nsys * jsz * 8)) return fail(NBG_ERR_NOMEM, "jac_step allocation failed");
+  return 0;
+}
+
+int check_pair(const uint8_t* pair, int n) {
+  if (!pair) return 0;
+  for (int q = 0; q < n * n; ++q)
+    if (pair[q]) return fail(NBG_ERR_UNSUPPORTED, "s.pair must be all-false (kickfast!/phic! pairs are not built yet)");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t nbg_version(void) { return 100; }
+const char* nbg_last_error(void) { return g_err.c_str(); }
+int32_t nbg_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t device, int64_t stream_budget_bytes) {
+  if (!out) return fail(NBG_ERR_ARG, "plan pointer is NULL");
+  *out = nullptr;
+  if (nbody < 2 || nbody > NBG_MAX_BODIES) return fail(NBG_ERR_ARG, "nbody must be in 2..16");
+  if (nsys < 1) return fail(NBG_ERR_ARG, "nsys must be >= 1");
+  int ndev = nbg_device_count();
+  if (ndev == 0) return fail(NBG_ERR_NO_DEVICE, "no CUDA device: libnbgrad_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(NBG_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  nbg_plan* p = new nbg_plan();
+  p->n = nbody; p->nsys = nsys; p->device = device;
+  p->ld = (size_t)((nsys + 31) / 32 * 32);
+  CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (stream_budget_bytes <= 0) {
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    stream_budget_bytes = (int64_t)(fr / 4);
+  }
+  p->stream_budget = stream_budget_bytes;
+  if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
+  CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
+  *out = p;
+  return NBG_OK;
+}
+
+int32_t nbg_plan_destroy(nbg_plan* p) {
+  if (!p) return NBG_OK;
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->stream);
+  DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
+                   &p->bstream, &p->bevlist, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
+                   &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters};
+  for (auto* b : all) b->release();
+  for (auto& b : p->stage) b.release();
+  cudaStreamDestroy(p->stream);
+  delete p;
+  return NBG_OK;
+}
+
+int32_t nbg_set_state(nbg_plan* p, const double* x, const double* v, const double* m, double t0, const double* xerror, const double* verror,
+                      const double* jac_step, const double* jac_error, const double* dqdt) {
+  if (!p || !x || !v || !m) return fail(NBG_ERR_ARG, "plan, x, v, m are required");
+  CK(cudaSetDevice(p->device));
+  const size_t n = p->n, nsys = p->nsys, M = 7 * n;
+  const double* src[6] = {x, v, m, xerror, verror, dqdt};
+  const size_t cnt[6] = {3 * n, 3 * n, n, 3 * n, 3 * n, M};
+  double* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int q = 0; q < 6; ++q) {
+    if (!src[q]) continue;
+    if (p->stage[q].ensure(cnt[q] * nsys * 8)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
+    CK(cudaMemcpyAsync(p->stage[q].p, src[q], cnt[q] * nsys * 8, cudaMemcpyHostToDevice, p->stream));
+    dev[q] = p->stage[q].as<double>();
+  }
+  const int tpb = 128;
+  pack_xvm_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], p->T, (int)n, (long)nsys, t0);
+  p->launches++;
+  CK(cudaMemsetAsync(p->bterr.p, 0, p->ld * 8, p->stream));
+  // jac_step / jac_error: lazily created as identity / zero unless supplied
+  p->jac_valid = false;
+  if (jac_step || jac_error) {
+    if (int r = ensure_jac(p)) return r;
+    const double* js[2] = {jac_step, jac_error};
+    double* dst[2] = {p->bJv.as<double>(), p->bJe.as<double>()};
+    for (int q = 0; q < 2; ++q) {
+      double* d = nullptr;
+      if (js[q]) {
+        if (p->stage[6].ensure(M * M * nsys * 8)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
+        CK(cudaMemcpyAsync(p->stage[6].p, js[q], M * M * nsys * 8, cudaMemcpyHostToDevice, p->stream));
+        d = p->stage[6].as<double>();
+      }
+      jac_from_julia_kernel<<<(unsigned)nsys, 256, 0, p->stream>>>(d, dst[q], (int)n, q);
+      p->launches++;
+      CK(cudaStreamSynchronize(p->stream));
+    }
+    p->jac_valid = true;
+  }
+  CK(cudaStreamSynchronize(p->stream));
+  p->has_state = true;
+  p->have_transit = false;
+  return NBG_OK;
+}
+
+static int make_jac_identity(nbg_plan* p) {
+  if (p->jac_valid) return 0;
+  if (int r = ensure_jac(p)) return r;
+  jac_from_julia_kernel<<<(unsigned)p->nsys, 256, 0, p->stream>>>(nullptr, p->bJv.as<double>(), p->n, 0);
+  jac_from_julia_kernel<<<(unsigned)p->nsys, 256, 0, p->stream>>>(nullptr, p->bJe.as<double>(), p->n, 1);
+  p->launches += 2;
+  p->jac_valid = true;
+  return 0;
+}
+
+int32_t nbg_get_state(nbg_plan* p, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error, double* dqdt, double* t,
+                      uint32_t* status) {
+  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  CK(cudaSetDevice(p->device));
+  const size_t n = p->n, nsys = p->nsys, M = 7 * n;
+  double* outs[5] = {x, v, xerror, verror, dqdt};
+  const size_t cnt[5] = {3 * n, 3 * n, 3 * n, 3 * n, M};
+  double* dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int q = 0; q < 5; ++q)
+    if (outs[q]) {
+      if (p->stage[q].ensure(cnt[q] * nsys * 8)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
+      dev[q] = p->stage[q].as<double>();
+    }
+  const int tpb = 128;
+  unpack_xv_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T, (int)n, (long)nsys, dev[0], dev[1], dev[2], dev[3], dev[4]);
+  p->launches++;
+  for (int q = 0; q < 5; ++q)
+    if (outs[q]) CK(cudaMemcpyAsync(outs[q], dev[q], cnt[q] * nsys * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (jac_step || jac_error) {
+    if (int r = make_jac_identity(p)) return r;
+    double* js[2] = {jac_step, jac_error};
+    const double* srcs[2] = {p->bJv.as<double>(), p->bJe.as<double>()};
+    for (int q = 0; q < 2; ++q)
+      if (js[q]) {
+        if (p->stage[6].ensure(M * M * nsys * 8)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
+        jac_to_julia_kernel<<<(unsigned)nsys, 256, 0, p->stream>>>(srcs[q], p->stage[6].as<double>(), (int)n, q);
+        p->launches++;
+        CK(cudaMemcpyAsync(js[q], p->stage[6].p, M * M * nsys * 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+      }
+  }
+  if (t) CK(cudaMemcpyAsync(t, p->bt.p, nsys * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (status) CK(cudaMemcpyAsync(status, p->bstatus.p, nsys * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return NBG_OK;
+}
+
+static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e1) {
+  for (double& q : p->timings) q = 0;
+  tm.collect(p->timings);
+  float tot = 0;
+  cudaEventElapsedTime(&tot, e0, e1);
+  p->timings[4] = tot;
+  p->timings[3] = tot - p->timings[0] - p->timings[1] - p->timings[2];
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  unsigned long long dc[8];
+  cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);
+  for (int q = 1; q <= 3; ++q) p->counters_host[q] = dc[q];
+  p->counters_host[5] = p->counters_host[5];
+}
+
+int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_last, int32_t grad, int32_t time_mode, double t_final) {
+  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  if (nsteps < 0) return fail(NBG_ERR_ARG, "nsteps must be >= 0");
+  CK(cudaSetDevice(p->device));
+  if (grad) if (int r = make_jac_identity(p)) return r;
+  if (time_mode == 0) CK(cudaMemsetAsync(p->bterr.p, 0, p->ld * 8, p->stream));  // s2 = zero(T): Integrator.jl:212
+  Timer tm{p->stream};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, p->stream);
+  if (int r = run_steps(p, h, (long)nsteps, grad != 0, false, 0, 0.0, h, time_mode == 0, tm, 0.0)) return r;
+  if (h_last != 0.0)
+    if (int r = run_steps(p, h_last, 1, grad != 0, false, 0, 0.0, h_last, time_mode == 0, tm, 0.0)) return r;
+  if (time_mode == 1) {
+    std::vector<double> tv(p->nsys, t_final);
+    CK(cudaMemcpyAsync(p->bt.p, tv.data(), p->nsys * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  }
+  cudaEventRecord(e1, p->stream);
+  CK(cudaStreamSynchronize(p->stream));
+  finish_timings(p, tm, e0, e1);
+  CK(cudaGetLastError());
+  return NBG_OK;
+}
+
+int32_t nbg_integrate(nbg_plan* p, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0, double h, int64_t nsteps,
+                      double h_last, int32_t grad, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error,
+                      double* dqdt, uint32_t* status) {
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (int r = check_pair(pair, p->n)) return r;
+  if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
+  if (int r = nbg_integrate_resident(p, h, nsteps, h_last, grad, 0, 0.0)) return r;
+  return nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, nullptr, status);
+}
+
+int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad,
+                                    const double* jac_init) {
+  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  if (!ntt_body) return fail(NBG_ERR_ARG, "ntt_body is required");
+  if (ti < 0 || ti >= p->n) return fail(NBG_ERR_ARG, "ti out of range");
+  if (mode != 0 && mode != 1) return fail(NBG_ERR_ARG, "mode must be 0 (TransitTiming) or 1 (TransitParameters)");
+  if (h == 0.0) return fail(NBG_ERR_ARG, "h must be non-zero");
+  CK(cudaSetDevice(p->device));
+  const int n = p->n;
+  const size_t nsys = p->nsys, M = 7 * n;
+  int RT = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ntt_body[i] < 0) return fail(NBG_ERR_ARG, "ntt_body must be >= 0");
+    p->ntt_body[i] = ntt_body[i]; p->off[i] = RT; RT += ntt_body[i];
+  }
+  p->RT = RT; p->C = mode == 1 ? 3 : 1;
+  const size_t C = p->C;
+  if (p->btt.ensure(std::max<size_t>(8, nsys * RT * C * 8))) return fail(NBG_ERR_NOMEM, "tt allocation failed");
+  CK(cudaMemsetAsync(p->btt.p, 0, nsys * RT * C * 8, p->stream));
+  if (grad) {
+    if (p->bdtdq0.ensure(std::max<size_t>(8, nsys * RT * M * C * 8))) return fail(NBG_ERR_NOMEM, "dtdq0 allocation failed (reduce ntt_body or the batch)");
+    CK(cudaMemsetAsync(p->bdtdq0.p, 0, nsys * RT * M * C * 8, p->stream));
+    if (int r = make_jac_identity(p)) return r;
+  }
+  CK(cudaMemcpyAsync(p->bntt.p, p->ntt_body, n * 4, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->boff.p, p->off, n * 4, cudaMemcpyHostToDevice, p->stream));
+  // t0 is s.t[1] of the resident state (identical for all systems of a batch)
+  double t0 = 0;
+  CK(cudaMemcpyAsync(&t0, p->bt.p, 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  const long nsteps = std::labs((long)std::nearbyint(tmax / h));         // Transits.jl:143
+  const double hs = h * check_step(t0, tmax + t0);                       // Transits.jl:144
+  Timer tm{p->stream};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, p->stream);
+  const int tpb = 128;
+  gsave_init_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T, n, (long)nsys, ti);
+  p->launches++;
+  double rate = nsteps > 0 ? (double)RT / (double)nsteps : 1.0;
+  if (int r = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate)) return r;
+  p->have_transit = true;
+  p->transit_grad = grad != 0;
+  p->have_dtde = false;
+  if (grad && jac_init) {
+    if (p->bjinit.ensure(nsys * M * M * 8) || p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
+      return fail(NBG_ERR_NOMEM, "dtdelements allocation failed");
+    CK(cudaMemcpyAsync(p->bjinit.p, jac_init, nsys * M * M * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemsetAsync(p->bdtde.p, 0, nsys * RT * M * C * 8, p->stream));
+    CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * M * 8)));
+    dtdelements_kernel<<<(unsigned)nsys, 256, M * M * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
+                                                                     p->bcount.as<int32_t>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), n, p->ld, RT,
+                                                                     (int)C);
+    p->launches++;
+    p->have_dtde = true;
+  }
+  cudaEventRecord(e1, p->stream);
+  CK(cudaStreamSynchronize(p->stream));
+  finish_timings(p, tm, e0, e1);
+  CK(cudaGetLastError());
+  return NBG_OK;
+}
+
+int32_t nbg_transit_fetch(nbg_plan* p, double* tt, int64_t* count, double* dtdq0, double* dtdelements) {
+  if (!p || !p->have_transit) return fail(NBG_ERR_ARG, "no transit results");
+  CK(cudaSetDevice(p->device));
+  const size_t nsys = p->nsys, M = 7 * p->n, C = p->C, RT = p->RT;
+  if (tt) CK(cudaMemcpyAsync(tt, p->btt.p, nsys * RT * C * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (count) {
+    if (p->stage[7].ensure(nsys * p->n * 8)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
+    const int tpb = 128;
+    count_out_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->bcount.as<int32_t>(), p->ld, p->n, (long)nsys, p->stage[7].as<int64_t>());
+    p->launches++;
+    CK(cudaMemcpyAsync(count, p->stage[7].p, nsys * p->n * 8, cudaMemcpyDeviceToHost, p->stream));
+  }
+  if (dtdq0 && p->transit_grad) CK(cudaMemcpyAsync(dtdq0, p->bdtdq0.p, nsys * RT * M * C * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (dtdelements && p->have_dtde) CK(cudaMemcpyAsync(dtdelements, p->bdtde.p, nsys * RT * M * C * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return NBG_OK;
+}
+
+int32_t nbg_transit_timing(nbg_plan* p, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0, double h, double tmax,
+                           int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad, const double* jac_init, double* tt, int64_t* count,
+                           double* dtdq0, double* dtdelements, double* x, double* v, double* xerror, double* verror, double* jac_step,
+                           double* jac_error, double* dqdt, double* t, uint32_t* status) {
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (int r = check_pair(pair, p->n)) return r;
+  if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
+  if (int r = nbg_transit_timing_resident(p, h, tmax, ti, ntt_body, mode, grad, jac_init)) return r;
+  if (int r = nbg_transit_fetch(p, tt, count, dtdq0, dtdelements)) return r;
+  return nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, t, status);
+}
+
+int32_t nbg_counters(nbg_plan* p, int64_t* c8) {
+  if (!p || !c8) return fail(NBG_ERR_ARG, "NULL argument");
+  for (int q = 0; q < 8; ++q) c8[q] = (int64_t)p->counters_host[q];
+  c8[4] = p->launches;
+  c8[5] = (int64_t)(p->counters_host[5] + p->counters_host[2]);
+  return NBG_OK;
+}
+int32_t nbg_counters_reset(nbg_plan* p) {
+  if (!p) return fail(NBG_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(p->device));
+  for (auto& q : p->counters_host) q = 0;
+  p->launches = 0;
+  CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  return NBG_OK;
+}
+int32_t nbg_last_timings(nbg_plan* p, double* ms5) {
+  if (!p || !ms5) return fail(NBG_ERR_ARG, "NULL argument");
+  for (int q = 0; q < 5; ++q) ms5[q] = p->timings[q];
+  return NBG_OK;
+}
+int64_t nbg_cuda_stream(nbg_plan* p) { return p ? (int64_t)(intptr_t)p->stream : 0; }
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// One AHL21 step of one planetary system by ONE thread (lanes of a warp = different systems):
+// positions/velocities with Kahan compensation, dq/dh, and -- when EMIT -- the stream of
+// per-pair linear operators that the Jacobian kernel (nbg_jacobian.cuh) applies to the 7N x 7N matrix.
+//
+// Replaces, for this path,
+//   ahl21!(s,d::Derivatives,h)    src/integrator/ahl21/ahl21.jl:5-95   (x, v, dqdt part; Jacobian part is streamed)
+//   ahl21!(s,h)                   src/integrator/ahl21/ahl21_no_grad.jl:6-18 (GRAD=false)
+//   drift!/drift_grad!            ahl21_no_grad.jl:24-29, ahl21.jl:318-331
+//   kepler_driftij_gamma!         ahl21.jl:706-760, ahl21_no_grad.jl:192-212
+//   phisalpha!                    ahl21.jl:558-700, ahl21_no_grad.jl:110-158
+// kickfast!/phic! act only on pairs flagged in s.pair, which is all-false unless set by hand
+// (Integrator.jl:91); this build requires pair == all-false (checked at the C ABI).
+//
+// Why x, v, dqdt never need the Jacobian: every Jacobian update in the reference is a left
+// multiplication of jac_step by an operator built from x, v, m only, and dqdt obeys the same recurrence
+// as one extra column.  So this thread advances the state and describes the operators; a thread group
+// per system applies them (column per thread) in a separate kernel.
+#pragma once
+#include "nbg_kepler.cuh"
+
+namespace nbg {
+
+constexpr int NMAX = 16;  // max bodies per system
+constexpr int KF = 64;    // doubles per Kepler-pair operator record
+constexpr int PF = 24;    // doubles per phisalpha-pair operator record
+
+// Kepler record fields
+constexpr int KF_K = 0;      // 36: jac_kepler[r][c], r,c < 6  (index 6*r + c)
+constexpr int KF_MI = 36;    // m_i/(m_i+m_j)
+constexpr int KF_MJ = 37;    // m_j/(m_i+m_j)
+constexpr int KF_CI7 = 38;   // 6: jac_ij[rows i][col m_i]
+constexpr int KF_CJ7 = 44;   // 6: jac_ij[rows j][col m_i]
+constexpr int KF_CI14 = 50;  // 6: jac_ij[rows i][col m_j]
+constexpr int KF_CJ14 = 56;  // 6: jac_ij[rows j][col m_j]
+// phisalpha record fields
+constexpr int PF_R = 0;      // 3: r_ij
+constexpr int PF_G3 = 3;     // G / r^3
+constexpr int PF_FAC1 = 4;   // coeff / r^5
+constexpr int PF_R2 = 5;     // r^2
+constexpr int PF_US = 6;     // 2 G fac1 / r   (mass-sum derivative is US * r_ij)
+constexpr int PF_RM = 7;     // 9: dF/dr [k][p]  (index 3*k + p)
+constexpr int PF_F = 16;     // 3: F_ij
+constexpr int PF_MI = 19;    // m_i
+constexpr int PF_MJ = 20;    // m_j
+
+__host__ __device__ inline int npairs(int n) { return n * (n - 1) / 2; }
+// doubles per system per step in the operator stream
+__host__ __device__ inline size_t step_fields(int n) { return (size_t)npairs(n) * (2 * KF + PF); }
+
+struct Body {
+  double x[3 * NMAX], v[3 * NMAX], xe[3 * NMAX], ve[3 * NMAX], m[NMAX];
+};
+
+// Operator-stream writer: element (field f) of this thread's system/slot lives at base[f * stride + idx].
+struct Emit {
+  double* base;
+  size_t stride;
+  size_t idx;
+  __device__ __forceinline__ void put(size_t f, double val) const { base[f * stride + idx] = val; }
+};
+
+template <bool GRAD, bool EMIT>
+__device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, double h2, bool drift_first, const Emit& em, size_t rec_base) {
+  double x0[3], v0[3], dl[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { x0[k] = b.x[3 * i + k] - b.x[3 * j + k]; v0[k] = b.v[3 * i + k] - b.v[3 * j + k]; }
+  const double msum = b.m[i] + b.m[j];
+  const double gm = kG * msum;
+  KepJac J;
+  if (gm == 0.0) {
+    // Two massless bodies: no interaction.  (The reference returns before touching anything, ahl21.jl:713,
+    // and then re-applies the previous pair's stale jac_ij; here the pair is the identity.)
+    if (EMIT) for (int f = 0; f < KF; ++f) em.put(rec_base + f, 0.0);
+    return;
+  }
+  kepler_pair<GRAD>(x0, v0, gm, h2, drift_first, dl, &J);
+  const double mijinv = 1.0 / msum;
+  const double mi = b.m[i] * mijinv, mj = b.m[j] * mijinv;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ksum(b.x[3 * i + k], b.xe[3 * i + k], mj * dl[k]);
+    ksum(b.x[3 * j + k], b.xe[3 * j + k], -mi * dl[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ksum(b.v[3 * i + k], b.ve[3 * i + k], mj * dl[3 + k]);
+    ksum(b.v[3 * j + k], b.ve[3 * j + k], -mi * dl[3 + k]);
+  }
+  if (GRAD) {
+    // dqdt_ij = dqdt_ij/2 + dqdt_old + jac_ij * dqdt_old   (ahl21.jl:38-40); mass entries of dqdt are identically 0
+    double dd[6], w[6];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) dd[l] = dq[6 * i + l] - dq[6 * j + l];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) s += J.jk[r][l] * dd[l];
+      w[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      dq[6 * i + r] = 0.5 * (mj * J.jk[r][7]) + dq[6 * i + r] + mj * w[r];
+      dq[6 * j + r] = 0.5 * (-mi * J.jk[r][7]) + dq[6 * j + r] - mi * w[r];
+    }
+  }
+  if (EMIT) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) em.put(rec_base + KF_K + 6 * r + c, J.jk[r][c]);
+    em.put(rec_base + KF_MI, mi);
+    em.put(rec_base + KF_MJ, mj);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      em.put(rec_base + KF_CI7 + r, J.jm[r] * b.m[j]);
+      em.put(rec_base + KF_CJ7 + r, -mj * dl[r] * mijinv - kG * mi * J.jk[r][6]);
+      em.put(rec_base + KF_CI14 + r, mi * dl[r] * mijinv + kG * mj * J.jk[r][6]);
+      em.put(rec_base + KF_CJ14 + r, -J.jm[r] * b.m[i]);
+    }
+  }
+}
+
+// phisalpha!(s,d,h,alpha=2): velocity kick m_j F_ij / -m_i F_ij per pair, with
+//   F_ij = fac1 (r fac2 - r^2 a_ij),  fac1 = coeff / r^5,  fac2 = 2 G (m_i+m_j)/r + 3 a_ij.r,  a_i = -sum_d G m_d r_id / r_id^3.
+// Its Jacobian is applied in factored form (same linear operator as the reference's dense jac_phi):
+//   da_i = - sum_d m_d Gam_id (dx_i - dx_d) - sum_d gam_id dm_d,      Gam = G (I/r^3 - 3 r r^T / r^5),  gam = G r / r^3
+//   dF_ij = Rm_ij (dx_i - dx_j) + fac1 (3 r r^T - r^2 I) (da_i - da_j) + US r (dm_i + dm_j)
+//   dv_i += m_j dF_ij + F_ij dm_j ;  dv_j -= m_i dF_ij + F_ij dm_i.
+template <bool GRAD, bool EMIT>
+__device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, double h, const Emit& em, size_t rec_base) {
+  double a[3 * NMAX], da[3 * NMAX];
+  for (int q = 0; q < 3 * n; ++q) { a[q] = 0.0; da[q] = 0.0; }
+  const double coeff = 2.0 * (h * h * h) / 96.0 * 2.0 * kG;  // alpha = 2  (ahl21.jl:564)
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      double r[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r[k] = b.x[3 * i + k] - b.x[3 * j + k];
+      const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+      const double r3 = r2 * sqrt(r2);
+      const double fac2 = kG / r3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double fac = fac2 * r[k];
+        a[3 * i + k] -= b.m[j] * fac;
+        a[3 * j + k] += b.m[i] * fac;
+      }
+      if (GRAD) {
+        double w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = dq[6 * i + k] - dq[6 * j + k];
+        const double rw = r[0] * w[0] + r[1] * w[1] + r[2] * w[2];
+        const double f3 = 3.0 * fac2 / r2 * rw;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double gw = fac2 * w[k] - f3 * r[k];
+          da[3 * i + k] -= b.m[j] * gw;
+          da[3 * j + k] += b.m[i] * gw;
+        }
+      }
+    }
+  double dvacc[3 * NMAX];
+  if (GRAD) for (int q = 0; q < 3 * n; ++q) dvacc[q] = 0.0;
+  int p = 0;
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = i + 1; j < n; ++j, ++p) {
+      double r[3], aij[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { aij[k] = a[3 * i + k] - a[3 * j + k]; r[k] = b.x[3 * i + k] - b.x[3 * j + k]; }
+      const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+      const double r1 = sqrt(r2);
+      const double ardot = aij[0] * r[0] + aij[1] * r[1] + aij[2] * r[2];
+      const double fac1 = coeff / (r2 * r2 * r1);
+      const double gmu = kG * (b.m[i] + b.m[j]);
+      const double fac2 = 2.0 * gmu / r1 + 3.0 * ardot;
+      double F[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        F[k] = fac1 * (r[k] * fac2 - r2 * aij[k]);
+        ksum(b.v[3 * i + k], b.ve[3 * i + k], b.m[j] * F[k]);
+        ksum(b.v[3 * j + k], b.ve[3 * j + k], -b.m[i] * F[k]);
+      }
+      if (GRAD || EMIT) {
+        double Rm[3][3];
+        const double r2inv = 1.0 / r2;
+        const double gr3 = gmu / (r2 * r1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double f5 = -5.0 * F[k] * r2inv;
+          const double fd = -2.0 * fac1 * (r[k] * gr3 + aij[k]);
+          const double f3r = 3.0 * fac1 * r[k];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) Rm[k][q] = f5 * r[q] + fd * r[q] + f3r * aij[q] + (k == q ? fac1 * fac2 : 0.0);
+        }
+        if (GRAD) {
+          double w[3], wa[3], dF[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { w[k] = dq[6 * i + k] - dq[6 * j + k]; wa[k] = da[3 * i + k] - da[3 * j + k]; }
+          const double rwa = r[0] * wa[0] + r[1] * wa[1] + r[2] * wa[2];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            dF[k] = Rm[k][0] * w[0] + Rm[k][1] * w[1] + Rm[k][2] * w[2] + fac1 * (3.0 * r[k] * rwa - r2 * wa[k]);
+            // dqdt_phi (explicit h-dependence, coeff ~ h^3) + jac_phi * dqdt   (ahl21.jl:632-633, :51-52)
+            dvacc[3 * i + k] += b.m[j] * (3.0 / h * F[k] + dF[k]);
+            dvacc[3 * j + k] -= b.m[i] * (3.0 / h * F[k] + dF[k]);
+          }
+        }
+        if (EMIT) {
+          const size_t rb = rec_base + (size_t)p * PF;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { em.put(rb + PF_R + k, r[k]); em.put(rb + PF_F + k, F[k]); }
+          em.put(rb + PF_G3, kG / (r2 * r1));
+          em.put(rb + PF_FAC1, fac1);
+          em.put(rb + PF_R2, r2);
+          em.put(rb + PF_US, 2.0 * kG * fac1 / r1);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) em.put(rb + PF_RM + 3 * k + q, Rm[k][q]);
+          em.put(rb + PF_MI, b.m[i]);
+          em.put(rb + PF_MJ, b.m[j]);
+        }
+      }
+    }
+  if (GRAD) for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dq[6 * i + 3 + k] += dvacc[3 * i + k];
+}
+
+// dq: d(state)/dh, 6 entries per body (x then v); mass entries are identically zero and not stored.
+// em.base points at this step's region of the operator stream (used when EMIT).
+template <bool GRAD, bool EMIT>
+__device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em) {
+  const double h2 = 0.5 * h;
+  const int P = npairs(n);
+  // fill!(s.dqdt,0); kickfast! (no kicked pairs); drift_grad!/drift!; dqdt[x] = v/2 + h2 dqdt[v]   (ahl21.jl:8-21)
+  for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ksum(b.x[3 * i + k], b.xe[3 * i + k], h2 * b.v[3 * i + k]);
+      if (GRAD) { dq[6 * i + k] = 0.5 * b.v[3 * i + k]; dq[6 * i + 3 + k] = 0.0; }
+    }
+  }
+  int rec = 0;
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = i + 1; j < n; ++j, ++rec) pair_section<GRAD, EMIT>(b, dq, i, j, h2, true, em, (size_t)rec * KF);
+  phisalpha_section<GRAD, EMIT>(b, dq, n, h, em, (size_t)2 * P * KF);
+  for (int i = n - 2; i >= 0; --i)
+    for (int j = n - 1; j >= i + 1; --j, ++rec) pair_section<GRAD, EMIT>(b, dq, i, j, h2, false, em, (size_t)rec * KF);
+  for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ksum(b.x[3 * i + k], b.xe[3 * i + k], h2 * b.v[3 * i + k]);
+      if (GRAD) dq[6 * i + k] += 0.5 * b.v[3 * i + k] + h2 * dq[6 * i + 3 + k];
+    }
+  }
+}
+
+// timing.jl:141-150  g!, gd!   (i = transited body, j = occultor)
+__device__ __forceinline__ double gsky(const Body& b, int i, int j) {
+  return (b.x[3 * j] - b.x[3 * i]) * (b.v[3 * j] - b.v[3 * i]) + (b.x[3 * j + 1] - b.x[3 * i + 1]) * (b.v[3 * j + 1] - b.v[3 * i + 1]);
+}
+__device__ __forceinline__ double gdot(const Body& b, const double* dq, int i, int j) {
+  return ((b.x[3 * j] - b.x[3 * i]) * (dq[6 * j + 3] - dq[6 * i + 3]) + (b.x[3 * j + 1] - b.x[3 * i + 1]) * (dq[6 * j + 4] - dq[6 * i + 4]) +
+          (b.v[3 * j] - b.v[3 * i]) * (dq[6 * j] - dq[6 * i]) + (b.v[3 * j + 1] - b.v[3 * i + 1]) * (dq[6 * j + 1] - dq[6 * i + 1]));
+}
+
+}  // namespace nbg

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's driver API for the hot path, over the C ABI (include/nbgrad.h).
+
+  State                 src/integrator/Integrator.jl:49-103
+  Integrator            src/integrator/Integrator.jl:17-31, callable forms :159-247
+  TransitTiming         src/transits/Transits.jl:14-56
+  TransitParameters     src/transits/Transits.jl:68-110
+  (intr)(s, tt; grad)   src/transits/Transits.jl:140-180
+
+Same names, argument meaning and error behaviour; every object carries a leading batch axis B (B = 1 is the
+reference's single-system call).  Index order is numpy's, i.e. the reverse of Julia's and 0-based:
+Julia s.x[k,i] -> s.x[b,i,k];  jac_step[r,c] -> s.jac_step[b,r,c];  tt.tt[i,k] -> tt.tt[b,i,k];
+tt.dtdq0[i,k,q,p] -> tt.dtdq0[b,i,k,q,p];  body indices (ti, occs) are 0-based.
+All arithmetic of the path runs in libnbgrad_b200.so on the GPU; nothing here computes on the CPU.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def ahl21(*_a, **_k):
+    """Placeholder for the reference's scheme function ahl21! (the only scheme of this build)."""
+    raise _lib.NbgError("ahl21 is executed on the device through Integrator(...)")
+
+
+_plans = {}
+
+
+def _plan(n, nsys, device=0, stream_budget=0):
+    key = (n, nsys, device, stream_budget)
+    if key not in _plans:
+        p = C.c_void_p()
+        check(_lib.lib().nbg_plan_create(C.byref(p), C.c_int32(n), C.c_int64(nsys), C.c_int32(device), C.c_int64(stream_budget)))
+        _plans[key] = p
+    return _plans[key]
+
+
+def release_plans():
+    for p in _plans.values():
+        _lib.lib().nbg_plan_destroy(p)
+    _plans.clear()
+
+
+def check_step(t0, tmax):
+    """Integrator.jl:249-259."""
+    sg = lambda x: (x > 0) - (x < 0)
+    if abs(tmax) > abs(t0):
+        return sg(tmax)
+    if sg(tmax) != sg(t0):
+        return sg(tmax)
+    return -1 * sg(tmax)
+
+
+class State:
+    """State(ic) — Integrator.jl:82-103."""
+
+    def __init__(self, ic):
+        x, v, jac_init = ic.init_nbody()
+        B, n = x.shape[0], ic.nbody
+        M = 7 * n
+        self.n = n
+        self.nsys = B
+        self.x, self.v = np.ascontiguousarray(x), np.ascontiguousarray(v)
+        self.m = ic.m  # by reference, as in the reference (quirk: Integrator.jl:101)
+        self.t = np.full(B, float(ic.t0))
+        self.jac_step = np.broadcast_to(np.eye(M), (B, M, M)).copy()
+        self.jac_error = np.zeros((B, M, M))
+        self.dqdt = np.zeros((B, M))
+        self.dqdt_error = np.zeros((B, M))
+        self.jac_init = jac_init if jac_init is not None else np.zeros((B, 0, 0))
+        self.xerror = np.zeros((B, n, 3))
+        self.verror = np.zeros((B, n, 3))
+        self.pair = np.zeros((n, n), dtype=bool)
+        self.status = np.zeros(B, dtype=np.uint32)
+
+    def copy(self):
+        import copy
+        s = copy.copy(self)
+        for k, val in self.__dict__.items():
+            if isinstance(val, np.ndarray) and k != "m":
+                setattr(s, k, val.copy())
+        return s
+
+    def __repr__(self):  # Base.show(::State): Integrator.jl:137-143
+        f = lambda a: "finite" if np.all(np.isfinite(a)) else "infinite!"
+        return "State{Float64}:\nPositions  : %s\nVelocities : %s\nJacobian   : %s" % (f(self.x), f(self.v), f(self.jac_step))
+
+    # -- device transfer helpers
+    def _upload(self, plan, with_jac):
+        if self.pair.any():
+            raise _lib.NbgError("NBG_ERR_UNSUPPORTED: s.pair must be all-false (kickfast!/phic! pairs are not built yet)")
+        L = _lib.lib()
+        self._m_c = np.ascontiguousarray(self.m, dtype=np.float64)
+        js = np.ascontiguousarray(self.jac_step.transpose(0, 2, 1)) if with_jac else None
+        je = np.ascontiguousarray(self.jac_error.transpose(0, 2, 1)) if with_jac else None
+        check(L.nbg_set_state(plan, ptr(self.x), ptr(self.v), ptr(self._m_c), C.c_double(float(self.t[0])), ptr(self.xerror), ptr(self.verror),
+                              ptr(js), ptr(je), ptr(self.dqdt) if with_jac else None))
+
+    def _download(self, plan, with_jac):
+        L = _lib.lib()
+        B, M = self.nsys, 7 * self.n
+        js = np.empty((B, M, M)) if with_jac else None
+        je = np.empty((B, M, M)) if with_jac else None
+        check(L.nbg_get_state(plan, ptr(self.x), ptr(self.v), ptr(self.xerror), ptr(self.verror), ptr(js), ptr(je), ptr(self.dqdt) if with_jac else None,
+                              ptr(self.t), ptr(self.status)))
+        if with_jac:
+            self.jac_step[...] = js.transpose(0, 2, 1)
+            self.jac_error[...] = je.transpose(0, 2, 1)
+
+
+def dState(ic):
+    """dState(ic) — Integrator.jl:106-110; the Derivatives scratch lives on the device, so only the State is returned."""
+    return State(ic), None
+
+
+class _TransitOutput:
+    ncomp = 1
+
+    def __init__(self, tmax, ic, ti=0, ntt=None):
+        n = ic.nbody
+        if ntt is None:
+            if not hasattr(ic, "elements"):
+                raise TypeError("TransitTiming(tmax, ic) needs an ElementsIC (Transits.jl:42-45); pass ntt= for other ICs")
+            with np.errstate(divide="ignore", invalid="ignore"):
+                q = float(tmax) / ic.elements[:, :, 1]
+            fin = np.isfinite(q)
+            ntt = int(np.max(np.ceil(np.abs(q[fin]))) + 3)  # Transits.jl:44-45
+        B = ic.m.shape[0]
+        self.n, self.nsys, self.ntt, self.ti = n, B, int(ntt), int(ti)
+        self.occs = [i for i in range(n) if i != ti]
+        self.count = np.zeros((B, n), dtype=np.int64)
+        self._alloc(B, n, self.ntt)
+
+    def zero_out(self):  # zero_out!(tt): Transits.jl:127-134
+        for k, val in self.__dict__.items():
+            if isinstance(val, np.ndarray):
+                val[...] = 0
+
+
+class TransitTiming(_TransitOutput):
+    """TransitTiming(tmax, ic, ti) — tt[b,i,k], dtdq0[b,i,k,q,p], dtdelements[b,i,k,q,p], count[b,i]."""
+
+    def _alloc(self, B, n, ntt):
+        self.tt = np.zeros((B, n, ntt))
+        self.dtdq0 = np.zeros((B, n, ntt, 7, n))
+        self.dtdelements = np.zeros((B, n, ntt, 7, n))
+
+
+class TransitParameters(_TransitOutput):
+    """TransitParameters(tmax, ic, ti) — ttbv[b,c,i,k] (c = time, v_sky, b_sky^2), dtbvdq0[b,c,i,k,q,p], dtbvdelements."""
+    ncomp = 3
+
+    def _alloc(self, B, n, ntt):
+        self.ttbv = np.zeros((B, 3, n, ntt))
+        self.dtbvdq0 = np.zeros((B, 3, n, ntt, 7, n))
+        self.dtbvdelements = np.zeros((B, 3, n, ntt, 7, n))
+
+
+class Integrator:
+    """Integrator(h, tmax) | Integrator(h, t0, tmax) | Integrator(scheme, h, t0, tmax) — Integrator.jl:17-31."""
+
+    def __init__(self, *args, device=0, stream_budget=0):
+        if len(args) and callable(args[0]):
+            if args[0] is not ahl21:
+                raise _lib.NbgError("NBG_ERR_UNSUPPORTED: only the ahl21 scheme is built")
+            args = args[1:]
+        if len(args) == 2:
+            h, tmax = args
+            t0 = 0.0
+        elif len(args) == 3:
+            h, t0, tmax = args
+        else:
+            raise TypeError("Integrator(h, tmax) | Integrator(h, t0, tmax) | Integrator(scheme, h, t0, tmax)")
+        self.scheme, self.h, self.t0, self.tmax = ahl21, float(h), float(t0), float(tmax)
+        self.device, self.stream_budget = device, stream_budget
+        self.last_timings = None
+
+    def _p(self, s):
+        return _plan(s.n, s.nsys, self.device, self.stream_budget)
+
+    def _timings(self, plan):
+        ms = np.zeros(5)
+        check(_lib.lib().nbg_last_timings(plan, ptr(ms)))
+        self.last_timings = dict(traj_ms=ms[0], transit_ms=ms[1], jac_ms=ms[2], other_ms=ms[3], total_ms=ms[4])
+
+    def __call__(self, s, arg=None, grad=True):
+        if isinstance(arg, _TransitOutput):
+            return self._transits(s, arg, grad)
+        if isinstance(arg, (int, np.integer)) and not isinstance(arg, bool):
+            return self._nsteps(s, int(arg), grad)
+        if arg is None:
+            arg = float(s.t[0]) + self.tmax  # (intr)(s): Integrator.jl:247
+        return self._to_time(s, float(arg), grad)
+
+    # (intr)(s, time; grad) — Integrator.jl:159-197
+    def _to_time(self, s, time, grad):
+        t0 = float(s.t[0])
+        nsteps = abs(int(np.rint((time - t0) / self.h)))
+        h = self.h * check_step(t0, time)
+        tmax = t0 + (h * nsteps)
+        h_last = (time - tmax) if tmax != time else 0.0
+        plan = self._p(s)
+        s._upload(plan, grad)
+        check(_lib.lib().nbg_integrate_resident(plan, C.c_double(h), C.c_int64(nsteps), C.c_double(h_last), C.c_int32(1 if grad else 0),
+                                                C.c_int32(1), C.c_double(time)))
+        s._download(plan, grad)
+        self._timings(plan)
+
+    # (intr)(s, N; grad) — Integrator.jl:211-234
+    def _nsteps(self, s, N, grad):
+        h = self.h
+        if N < 0:
+            h, N = -h, -N
+        plan = self._p(s)
+        s._upload(plan, grad)
+        check(_lib.lib().nbg_integrate_resident(plan, C.c_double(h), C.c_int64(N), C.c_double(0.0), C.c_int32(1 if grad else 0), C.c_int32(0),
+                                                C.c_double(0.0)))
+        s._download(plan, grad)
+        self._timings(plan)
+
+    # (intr)(s, tt; grad) — Transits.jl:140-180
+    def _transits(self, s, tt, grad):
+        L = _lib.lib()
+        plan = self._p(s)
+        n, B, ntt, M = s.n, s.nsys, tt.ntt, 7 * s.n
+        s._upload(plan, grad)
+        ntt_body = np.full(n, ntt, dtype=np.int32)
+        mode = 1 if tt.ncomp == 3 else 0
+        ji = None
+        if grad and s.jac_init.size:
+            ji = np.ascontiguousarray(s.jac_init.transpose(0, 2, 1))
+        check(L.nbg_transit_timing_resident(plan, C.c_double(self.h), C.c_double(self.tmax), C.c_int32(tt.ti), ptr(ntt_body), C.c_int32(mode),
+                                            C.c_int32(1 if grad else 0), ptr(ji)))
+        Cn = tt.ncomp
+        shp_t = (B, n, ntt) if Cn == 1 else (B, n, ntt, 3)
+        shp_d = (B, n, ntt, n, 7) if Cn == 1 else (B, n, ntt, n, 7, 3)
+        t_raw = np.zeros(shp_t)
+        d_raw = np.zeros(shp_d) if grad else None
+        e_raw = np.zeros(shp_d) if (grad and ji is not None) else None
+        check(L.nbg_transit_fetch(plan, ptr(t_raw), ptr(tt.count), ptr(d_raw), ptr(e_raw)))
+        s._download(plan, grad)
+        if Cn == 1:
+            tt.tt[...] = t_raw
+            if grad:
+                tt.dtdq0[...] = d_raw.transpose(0, 1, 2, 4, 3)
+                if e_raw is not None:
+                    tt.dtdelements[...] = e_raw.transpose(0, 1, 2, 4, 3)
+        else:
+            tt.ttbv[...] = t_raw.transpose(0, 3, 1, 2)
+            if grad:
+                tt.dtbvdq0[...] = d_raw.transpose(0, 5, 1, 2, 4, 3)
+                if e_raw is not None:
+                    tt.dtbvdelements[...] = e_raw.transpose(0, 5, 1, 2, 4, 3)
+        self._timings(plan)
+
+
+def device_count():
+    return int(_lib.lib().nbg_device_count())

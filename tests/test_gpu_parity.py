@@ -1,0 +1,277 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the host mirror `nbgrad`) against the oracle on the same
+inputs.  Tolerance: relative 1e-11 in max-norm on transit times, final Cartesian state and Jacobian / dtdq0 /
+dtdelements entries (BASELINE.json north_star; stated because FMA contraction, libm and reduction order differ
+from the CPU path).  Run with `pytest -m gpu` on the B200 box."""
+import numpy as np
+import pytest
+
+from conftest import tilt
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+T0 = 7257.93115525
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=float); b = np.asarray(b, dtype=float)
+    d = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) / (d if d > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nbgrad
+    assert nbgrad.device_count() >= 1, "no CUDA device"
+    return nbgrad
+
+
+def oracle_integrate(oracle, x, v, m, t0, h, **kw):
+    s = oracle.new_state(x, v, m, t0)
+    oracle.integrate(s, h, **kw)
+    return s
+
+
+def cartesian_ic(nb, x, v, m, t0):
+    coords = np.concatenate([np.asarray(m)[..., None], x, v], axis=-1)
+    return nb.CartesianIC(t0, coords.shape[-2], coords)
+
+
+def test_step_parity_3body_tilted(nb, oracle, elements):
+    # cfg 1 flavour (test_integrator.jl:2-40): 3 bodies, planet masses x100, tilted, 100 steps of 0.05 d, grad
+    el = elements[:3].copy(); el[1, 0] *= 100; el[2, 0] *= 100; el[:, 6] = 0
+    x, v, _ = oracle.init_nbody(el, T0)
+    x, v = tilt(x, v)
+    so = oracle_integrate(oracle, x, v, el[:, 0], T0, 0.05, time=T0 + 5.0, grad=True)
+    s = nb.State(cartesian_ic(nb, x, v, el[:, 0], T0))
+    nb.Integrator(nb.ahl21, 0.05, T0, 5.0)(s)
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+    assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+    assert rel(s.dqdt[0], so["dqdt"]) < TOL
+    assert s.t[0] == so["t"][0]
+    assert s.status[0] == 0
+
+
+def test_step_parity_trappist8(nb, oracle, elements):
+    x, v, _ = oracle.init_nbody(elements, 7257.0)
+    so = oracle_integrate(oracle, x, v, elements[:, 0], 7257.0, 0.06, nsteps=500, grad=True)
+    s = nb.State(cartesian_ic(nb, x, v, elements[:, 0], 7257.0))
+    nb.Integrator(0.06, 30.0)(s, 500)
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+    assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+    assert rel(s.jac_error[0], so["jac_err_cm"].T) < 1e-3  # compensation terms: same size, not same bits
+    assert rel(s.dqdt[0], so["dqdt"]) < TOL
+    assert abs(s.t[0] - so["t"][0]) < 1e-9
+
+
+def test_grad_and_nograd_positions_identical(nb, oracle, elements):
+    # test_integrator.jl:177-185 on the GPU: x, v bit-identical with and without derivatives
+    el = elements[:3].copy(); el[1, 0] *= 100; el[2, 0] *= 100; el[:, 6] = 0
+    ic = nb.ElementsIC(T0, 3, el)
+    sg, sn = nb.State(ic), nb.State(ic)
+    nb.Integrator(0.05, 200.0)(sn, grad=False)
+    nb.Integrator(0.05, 200.0)(sg, grad=True)
+    assert np.array_equal(sn.x, sg.x) and np.array_equal(sn.v, sg.v)
+    x, v, _ = oracle.init_nbody(el, T0)
+    so = oracle_integrate(oracle, x, v, el[:, 0], T0, 0.05, time=T0 + 200.0, grad=False)
+    assert rel(sn.x[0], so["x"]) < TOL and rel(sn.v[0], so["v"]) < TOL
+
+
+def test_backward_and_fractional_last_step(nb, oracle, elements):
+    el = elements[:4]
+    x, v, _ = oracle.init_nbody(el, 10.0)
+    for time in (10.0 + 1.23, 10.0 - 0.87):
+        so = oracle_integrate(oracle, x, v, el[:, 0], 10.0, 0.05, time=time, grad=True)
+        s = nb.State(cartesian_ic(nb, x, v, el[:, 0], 10.0))
+        nb.Integrator(0.05, 0.0)(s, time)
+        assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+        assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+        assert s.t[0] == time
+    so = oracle_integrate(oracle, x, v, el[:, 0], 10.0, 0.05, nsteps=-20, grad=True)
+    s = nb.State(cartesian_ic(nb, x, v, el[:, 0], 10.0))
+    nb.Integrator(0.05, 0.0)(s, -20)
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+    assert abs(s.t[0] - so["t"][0]) < 1e-12
+
+
+def test_resume_equals_single_run(nb, elements):
+    # State is the checkpoint: 60 + 40 steps == 100 steps, bit for bit (docs/src/basic.md:89-90)
+    ic = nb.ElementsIC(7257.0, 5, elements)
+    a, b = nb.State(ic), nb.State(ic)
+    intr = nb.Integrator(0.06, 6.0)
+    intr(a, 100)
+    intr(b, 60)
+    intr(b, 40)
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.v, b.v)
+    assert np.array_equal(a.jac_step, b.jac_step) and np.array_equal(a.jac_error, b.jac_error)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 12, 16])
+def test_nbody_sweep(nb, oracle, n):
+    # cfg 4 at test size: star + (n-1) planets m=3e-5, P_k = 1.5*1.6^(k-1), nested hierarchy, h=0.05, 40 steps, grad
+    el = np.zeros((n, 7)); el[0, 0] = 1.0
+    for k in range(1, n):
+        el[k] = [3e-5, 1.5 * 1.6 ** (k - 1), 0.1 * k, 0.01, 0.0, np.pi / 2, 0.0]
+    x, v, _ = oracle.init_nbody(el, 0.0)
+    so = oracle_integrate(oracle, x, v, el[:, 0], 0.0, 0.05, nsteps=40, grad=True)
+    s = nb.State(nb.ElementsIC(0.0, n, el))
+    nb.Integrator(0.05, 2.0)(s, 40)
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+    assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+    assert rel(s.dqdt[0], so["dqdt"]) < TOL
+
+
+def _tt_oracle(oracle, el, t0, h, tmax, ntt, ti=0, grad=True, ntbv=1):
+    x, v, jac = oracle.init_nbody(el, t0)
+    s = oracle.new_state(x, v, el[:, 0], t0)
+    r = oracle.transit_timing(s, h, tmax, ntt, ti=ti, grad=grad, jac_init=jac if grad else None, ntbv=ntbv)
+    return s, r
+
+
+def _cmp_tt(tt_gpu, count_gpu, r):
+    assert np.array_equal(count_gpu, r["count"])
+    mask = r["tt"] != 0
+    assert np.array_equal(mask, tt_gpu != 0)
+    assert np.max(np.abs(tt_gpu[mask] - r["tt"][mask]) / np.abs(r["tt"][mask])) < TOL
+
+
+def test_transit_timing_cfg1(nb, oracle, elements):
+    # cfg 1: rows 1-3 of elements.txt, t0 = 7257.93115525, h = 0.05, TransitTiming, grad
+    el = elements[:3]
+    h, tmax = 0.05, 20.0
+    ic = nb.ElementsIC(T0, 3, el)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s, tt)
+    so, r = _tt_oracle(oracle, el, T0, h, tmax, tt.ntt)
+    _cmp_tt(tt.tt[0], tt.count[0], r)
+    assert r["count"].sum() > 15
+    assert rel(tt.dtdq0[0], r["dtdq0"]) < TOL
+    assert rel(tt.dtdelements[0], r["dtdelements"]) < TOL
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+
+
+def test_transit_timing_trappist8_batch(nb, oracle, elements):
+    # cfg 2 at test size: 8 bodies, h = 0.06, 30 d, batch of perturbed systems
+    B, n, t0, h, tmax = 5, 8, 7257.0, 0.06, 30.0
+    rng = np.random.default_rng(20211582)
+    elb = np.broadcast_to(elements, (B, n, 7)).copy()
+    elb[1:, 1:, 0] *= 1 + 1e-4 * rng.standard_normal((B - 1, n - 1))
+    elb[1:, 1:, 1] *= 1 + 1e-4 * rng.standard_normal((B - 1, n - 1))
+    elb[1:, 1:, 3:5] += 1e-4 * rng.standard_normal((B - 1, n - 1, 2))
+    ic = nb.ElementsIC(t0, n, elb)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s, tt)
+    assert not s.status.any()
+    for b in range(B):
+        so, r = _tt_oracle(oracle, elb[b], t0, h, tmax, tt.ntt)
+        _cmp_tt(tt.tt[b], tt.count[b], r)
+        assert rel(tt.dtdq0[b], r["dtdq0"]) < TOL
+        assert rel(tt.dtdelements[b], r["dtdelements"]) < TOL
+        assert rel(s.x[b], so["x"]) < TOL and rel(s.v[b], so["v"]) < TOL
+        assert rel(s.jac_step[b], so["jac_step_cm"].T) < TOL
+    assert tt.count.sum() > 50 * B
+
+
+def test_transit_timing_nograd_equals_grad_times(nb, elements):
+    # test_transit_timing.jl:91-97 on the GPU
+    ic = nb.ElementsIC(7257.0, 4, elements)
+    sg, sn = nb.State(ic), nb.State(ic)
+    tg, tn = nb.TransitTiming(40.0, ic), nb.TransitTiming(40.0, ic)
+    nb.Integrator(0.05, 40.0)(sg, tg, grad=True)
+    nb.Integrator(0.05, 40.0)(sn, tn, grad=False)
+    assert tg.count.sum() > 20
+    assert np.array_equal(tg.tt, tn.tt) and np.array_equal(tg.count, tn.count)
+    assert not tn.dtdq0.any()
+
+
+def test_findtransit_known_answer_gpu(nb, elements):
+    # test_findtransit.jl on the GPU: first transit of each planet equals its t0 element to < 1e-6
+    n = 7
+    ic = nb.ElementsIC(7257.0, n, elements)
+    s, tt = nb.State(ic), nb.TransitTiming(10.0, ic)
+    nb.Integrator(nb.ahl21, 0.01, 7257.0, 10.0)(s, tt, grad=False)
+    for i in range(1, n):
+        assert abs((elements[i, 2] - tt.tt[0, i, 0]) / elements[i, 2]) < 1e-6
+
+
+@pytest.mark.parametrize("ti", [0, 1])
+def test_transit_parameters_and_ti(nb, oracle, elements, ti):
+    N, t0 = 3, T0 - 7300.0 - 0.5
+    el = elements[:N].copy(); el[1:, 2] -= 7300.0; el[:, 6] = 0; el[1, 0] *= 10; el[2, 0] *= 10
+    h, tmax = 0.04, 10.0
+    ic = nb.ElementsIC(t0, N, el)
+    s, tp = nb.State(ic), nb.TransitParameters(tmax, ic, ti)
+    nb.Integrator(h, tmax)(s, tp)
+    so, r = _tt_oracle(oracle, el, t0, h, tmax, tp.ntt, ti=ti, ntbv=3)
+    assert np.array_equal(tp.count[0], r["count"]) and r["count"].sum() > 0
+    mask = r["tt"][0] != 0
+    assert np.max(np.abs(tp.ttbv[0, 0][mask] - r["tt"][0][mask]) / np.abs(r["tt"][0][mask])) < TOL
+    assert rel(tp.ttbv[0, 1], r["tt"][1]) < TOL                      # v_sky
+    assert np.max(np.abs(tp.ttbv[0, 2] - r["tt"][2])) < 1e-11 * 1e-4  # b_sky^2 ~ 0 for this edge-on system: absolute
+    assert rel(tp.dtbvdq0[0, 0], r["dtdq0"][0]) < TOL
+    assert rel(tp.dtbvdq0[0, 1], r["dtdq0"][1]) < TOL
+    assert rel(tp.dtbvdelements[0, :2], r["dtdelements"][:2]) < TOL
+
+
+def test_outer_solar_system_nograd_energy(nb, oracle):
+    # cfg 3 at test size: 5-body outer solar system (examples/outer_ss_example.jl:16-48), grad=false, h = 25 d
+    from golden.outer_ss import outer_ss_cartesian, energy_angmom
+    m, x, v = outer_ss_cartesian()
+    B = 4
+    rng = np.random.default_rng(3)
+    xb = np.broadcast_to(x, (B, 5, 3)).copy(); xb[1:] *= 1 + 1e-8 * rng.standard_normal((B - 1, 5, 3))
+    vb = np.broadcast_to(v, (B, 5, 3)).copy()
+    mb = np.broadcast_to(m, (B, 5)).copy()
+    coords = np.concatenate([mb[..., None], xb, vb], axis=-1)
+    s = nb.State(nb.CartesianIC(0.0, 5, coords))
+    nsteps, h = 4000, 25.0
+    nb.Integrator(h, nsteps * h)(s, nsteps, grad=False)
+    for b in range(B):
+        so = oracle_integrate(oracle, xb[b], vb[b], m, 0.0, h, nsteps=nsteps, grad=False)
+        assert rel(s.x[b], so["x"]) < 1e-10 and rel(s.v[b], so["v"]) < 1e-10  # 4000 steps of h = 25 d: looser, stated
+        E0, L0 = energy_angmom(m, xb[b], vb[b])
+        E1, L1 = energy_angmom(m, s.x[b], s.v[b])
+        Eo, Lo = energy_angmom(m, so["x"], so["v"])
+        # energy / angular momentum drift no worse than the reference path (within 10% + rounding floor)
+        assert abs(E1 / E0 - 1) <= 1.1 * abs(Eo / E0 - 1) + 1e-13
+        assert np.linalg.norm(L1 - L0) / np.linalg.norm(L0) <= 1.1 * np.linalg.norm(Lo - L0) / np.linalg.norm(L0) + 1e-13
+
+
+def test_errors_are_loud(nb, elements):
+    ic = nb.ElementsIC(0.0, 3, elements)
+    s = nb.State(ic)
+    s.pair[0, 1] = True
+    with pytest.raises(nb.NbgError):
+        nb.Integrator(0.05, 1.0)(s, 2)
+    import ctypes as C
+    L = nb.lib()
+    p = C.c_void_p()
+    assert L.nbg_plan_create(C.byref(p), C.c_int32(1), C.c_int64(4), C.c_int32(0), C.c_int64(0)) == -1
+    assert L.nbg_plan_create(C.byref(p), C.c_int32(17), C.c_int64(4), C.c_int32(0), C.c_int64(0)) == -1
+    assert L.nbg_plan_create(C.byref(p), C.c_int32(3), C.c_int64(0), C.c_int32(0), C.c_int64(0)) == -1
+    assert L.nbg_plan_create(C.byref(p), C.c_int32(3), C.c_int64(4), C.c_int32(99), C.c_int64(0)) == -1
+    assert b"device" in L.nbg_last_error()
+
+
+def test_ntt_overflow_is_counted_not_stored(nb, elements):
+    # timing.jl:18-19: count keeps incrementing past ntt, the transit is dropped
+    ic = nb.ElementsIC(7257.0, 3, elements)
+    s = nb.State(ic)
+    tt = nb.TransitTiming(30.0, ic, 0, ntt=3)
+    nb.Integrator(0.05, 30.0)(s, tt)
+    assert tt.count[0, 1] > 3 and np.all(tt.tt[0, 1] != 0)
+    assert s.status[0] & 8
+    full = nb.TransitTiming(30.0, ic)
+    s2 = nb.State(ic)
+    nb.Integrator(0.05, 30.0)(s2, full)
+    assert np.array_equal(full.tt[0, 1, :3], tt.tt[0, 1]) and np.array_equal(full.count, tt.count)
+
+
+def test_small_event_chunks(nb, oracle, elements):
+    # tiny operator-stream budget -> one step per chunk; results must not depend on chunking
+    ic = nb.ElementsIC(7257.0, 4, elements)
+    a, b = nb.State(ic), nb.State(ic)
+    ta, tb = nb.TransitTiming(6.0, ic), nb.TransitTiming(6.0, ic)
+    nb.Integrator(0.05, 6.0)(a, ta)
+    nb.Integrator(0.05, 6.0, stream_budget=1)(b, tb)
+    assert np.array_equal(ta.tt, tb.tt) and np.array_equal(ta.dtdq0, tb.dtdq0) and np.array_equal(a.jac_step, b.jac_step)
