@@ -116,6 +116,9 @@ int32_t nbg_counters(nbg_plan* plan, int64_t* c8);
 int32_t nbg_counters_reset(nbg_plan* plan);
 int32_t nbg_last_timings(nbg_plan* plan, double* ms5);
 int64_t nbg_cuda_stream(nbg_plan* plan); /* cudaStream_t of the plan, for callers that time with their own events */
+/* FP64 (DFMA) pipe peak of `device`, measured with 8 independent FMA chains per thread: the roofline denominator
+ * for this path (the driver-written MEASURED_PEAKS.json carries HBM and bf16 figures only). */
+int32_t nbg_fp64_peak(int32_t device, double* tflops, double* ms);
 
 #ifdef __cplusplus
 }

@@ -351,6 +351,16 @@ __global__ void count_out_kernel(const int32_t* count, size_t ld, int n, long ns
   for (int i = 0; i < n; ++i) out[sys * n + i] = count[i * ld + sys];
 }
 
+// FP64 pipe peak: 8 independent DFMA chains per thread (roofline denominator; MEASURED_PEAKS.json has no FP64 entry)
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -851,5 +861,33 @@ int32_t nbg_last_timings(nbg_plan* p, double* ms5) {
   return NBG_OK;
 }
 int64_t nbg_cuda_stream(nbg_plan* p) { return p ? (int64_t)(intptr_t)p->stream : 0; }
+
+int32_t nbg_fp64_peak(int32_t device, double* tflops, double* ms) {
+  if (nbg_device_count() == 0) return fail(NBG_ERR_NO_DEVICE, "no CUDA device: libnbgrad_b200 has no CPU fallback");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (rep > 0 && t < best) best = t;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  return NBG_OK;
+}
 
 }  // extern "C"

@@ -152,11 +152,14 @@ __device__ __forceinline__ double H6f(double gamma, double beta) {
 // Result of one pair solve.  dx[0..2] = delta position, dx[3..5] = delta velocity (relative coordinates);
 // jk[r][c]: d(delxv[r]) / d(x0, v0, k, h)[c]  (6 x 8); jm[r]: cancellation-safe mass derivative (6).
 struct KepJac { double jk[6][8]; double jm[6]; };
+// the 22 scalars jac_delxv_gamma! hands to compute_jacobian_gamma! (ahl21.jl:888)
+struct KepScal { double gamma, g0, g1, g2, g3, h1, h2, dfdt, fm1, gmh, dgdtm1, r0, r, r0inv, rinv, k, h, beta, betainv, eta, sqb, zeta; };
 
-// jac_delxv_gamma! + compute_jacobian_gamma!.  k = G (m_i + m_j) != 0.
-template <bool GRAD>
-__device__ __noinline__ void kepler_pair(const double* __restrict__ x0, const double* __restrict__ v0, double k, double h, bool drift_first,
-                                         double* __restrict__ delxv, KepJac* __restrict__ J) {
+// jac_delxv_gamma! (ahl21.jl:766-890).  k = G (m_i + m_j) != 0.
+// NOT a template and never inlined: the grad and no-grad paths execute the very same instructions, which is what
+// makes x, v bit-identical between them (the reference asserts this: test/test_integrator.jl:184-185).
+__device__ __noinline__ void kepler_solve(const double* __restrict__ x0, const double* __restrict__ v0, double k, double h, bool drift_first,
+                                          double* __restrict__ delxv, KepScal* __restrict__ P) {
   const double rt0 = x0[0] - h * v0[0], rt1 = x0[1] - h * v0[1], rt2 = x0[2] - h * v0[2];
   const double r0 = drift_first ? sqrt(rt0 * rt0 + rt1 * rt1 + rt2 * rt2) : sqrt(x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2]);
   const double r0inv = 1.0 / r0;
@@ -221,9 +224,17 @@ __device__ __noinline__ void kepler_pair(const double* __restrict__ x0, const do
     delxv[j] = fm1 * x0[j] + gmh * v0[j];
     delxv[3 + j] = dfdt * x0[j] + dgdtm1 * v0[j];
   }
-  if (!GRAD) return;
+  P->gamma = gamma; P->g0 = g0; P->g1 = g1; P->g2 = g2; P->g3 = g3; P->h1 = h1; P->h2 = h2; P->dfdt = dfdt; P->fm1 = fm1; P->gmh = gmh;
+  P->dgdtm1 = dgdtm1; P->r0 = r0; P->r = r; P->r0inv = r0inv; P->rinv = rinv; P->k = k; P->h = h; P->beta = beta; P->betainv = betainv;
+  P->eta = eta; P->sqb = sqb; P->zeta = zeta;
+}
 
-  // ---- analytic Jacobian ----
+// compute_jacobian_gamma! (ahl21.jl:896-1139, debug = false)
+__device__ __noinline__ void kepler_jacobian(const KepScal* __restrict__ P, const double* __restrict__ x0, const double* __restrict__ v0,
+                                             bool drift_first, KepJac* __restrict__ J) {
+  const double gamma = P->gamma, g0 = P->g0, g1 = P->g1, g2 = P->g2, g3 = P->g3, h1 = P->h1, h2 = P->h2, dfdt = P->dfdt, fm1 = P->fm1,
+               gmh = P->gmh, dgdtm1 = P->dgdtm1, r0 = P->r0, r = P->r, r0inv = P->r0inv, rinv = P->rinv, k = P->k, h = P->h, beta = P->beta,
+               betainv = P->betainv, eta = P->eta, sqb = P->sqb, zeta = P->zeta;
   const double r0inv2 = r0inv * r0inv, r0inv3 = r0inv2 * r0inv;
   const double rinv2 = rinv * rinv, rinv3 = rinv2 * rinv;
   const double hsq = h * h, ksq = k * k;

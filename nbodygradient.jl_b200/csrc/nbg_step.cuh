@@ -73,7 +73,9 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
     if (EMIT) for (int f = 0; f < KF; ++f) em.put(rec_base + f, 0.0);
     return;
   }
-  kepler_pair<GRAD>(x0, v0, gm, h2, drift_first, dl, &J);
+  KepScal P;
+  kepler_solve(x0, v0, gm, h2, drift_first, dl, &P);
+  if (GRAD) kepler_jacobian(&P, x0, v0, drift_first, &J);
   const double mijinv = 1.0 / msum;
   const double mi = b.m[i] * mijinv, mj = b.m[j] * mijinv;
 #pragma unroll
@@ -127,11 +129,10 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
 //   da_i = - sum_d m_d Gam_id (dx_i - dx_d) - sum_d gam_id dm_d,      Gam = G (I/r^3 - 3 r r^T / r^5),  gam = G r / r^3
 //   dF_ij = Rm_ij (dx_i - dx_j) + fac1 (3 r r^T - r^2 I) (da_i - da_j) + US r (dm_i + dm_j)
 //   dv_i += m_j dF_ij + F_ij dm_j ;  dv_j -= m_i dF_ij + F_ij dm_i.
-template <bool GRAD, bool EMIT>
-__device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, double h, const Emit& em, size_t rec_base) {
-  double a[3 * NMAX], da[3 * NMAX];
-  for (int q = 0; q < 3 * n; ++q) { a[q] = 0.0; da[q] = 0.0; }
-  const double coeff = 2.0 * (h * h * h) / 96.0 * 2.0 * kG;  // alpha = 2  (ahl21.jl:564)
+// The pieces of phisalpha! that determine x, v are non-template and never inlined, so the grad and no-grad
+// paths run identical instructions (x, v bit-identical between them, as the reference asserts).
+__device__ __noinline__ void phis_accel(const Body& b, int n, double* __restrict__ a) {
+  for (int q = 0; q < 3 * n; ++q) a[q] = 0.0;
   for (int i = 0; i < n - 1; ++i)
     for (int j = i + 1; j < n; ++j) {
       double r[3];
@@ -146,10 +147,35 @@ __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, do
         a[3 * i + k] -= b.m[j] * fac;
         a[3 * j + k] += b.m[i] * fac;
       }
-      if (GRAD) {
-        double w[3];
+    }
+}
+// out = {F0, F1, F2, fac1, fac2, r2, r1}
+__device__ __noinline__ void phis_force(const double* __restrict__ r, const double* __restrict__ aij, double gmu, double coeff,
+                                        double* __restrict__ out) {
+  const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  const double r1 = sqrt(r2);
+  const double ardot = aij[0] * r[0] + aij[1] * r[1] + aij[2] * r[2];
+  const double fac1 = coeff / (r2 * r2 * r1);
+  const double fac2 = 2.0 * gmu / r1 + 3.0 * ardot;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) w[k] = dq[6 * i + k] - dq[6 * j + k];
+  for (int k = 0; k < 3; ++k) out[k] = fac1 * (r[k] * fac2 - r2 * aij[k]);
+  out[3] = fac1; out[4] = fac2; out[5] = r2; out[6] = r1;
+}
+
+template <bool GRAD, bool EMIT>
+__device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, double h, const Emit& em, size_t rec_base) {
+  double a[3 * NMAX], da[3 * NMAX];
+  const double coeff = 2.0 * (h * h * h) / 96.0 * 2.0 * kG;  // alpha = 2  (ahl21.jl:564)
+  phis_accel(b, n, a);
+  if (GRAD) {
+    for (int q = 0; q < 3 * n; ++q) da[q] = 0.0;
+    for (int i = 0; i < n - 1; ++i)
+      for (int j = i + 1; j < n; ++j) {
+        double r[3], w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r[k] = b.x[3 * i + k] - b.x[3 * j + k]; w[k] = dq[6 * i + k] - dq[6 * j + k]; }
+        const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        const double fac2 = kG / (r2 * sqrt(r2));
         const double rw = r[0] * w[0] + r[1] * w[1] + r[2] * w[2];
         const double f3 = 3.0 * fac2 / r2 * rw;
 #pragma unroll
@@ -159,25 +185,21 @@ __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, do
           da[3 * j + k] += b.m[i] * gw;
         }
       }
-    }
+  }
   double dvacc[3 * NMAX];
   if (GRAD) for (int q = 0; q < 3 * n; ++q) dvacc[q] = 0.0;
   int p = 0;
   for (int i = 0; i < n - 1; ++i)
     for (int j = i + 1; j < n; ++j, ++p) {
-      double r[3], aij[3];
+      double r[3], aij[3], fo[7];
 #pragma unroll
       for (int k = 0; k < 3; ++k) { aij[k] = a[3 * i + k] - a[3 * j + k]; r[k] = b.x[3 * i + k] - b.x[3 * j + k]; }
-      const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-      const double r1 = sqrt(r2);
-      const double ardot = aij[0] * r[0] + aij[1] * r[1] + aij[2] * r[2];
-      const double fac1 = coeff / (r2 * r2 * r1);
       const double gmu = kG * (b.m[i] + b.m[j]);
-      const double fac2 = 2.0 * gmu / r1 + 3.0 * ardot;
-      double F[3];
+      phis_force(r, aij, gmu, coeff, fo);
+      const double F[3] = {fo[0], fo[1], fo[2]};
+      const double fac1 = fo[3], fac2 = fo[4], r2 = fo[5], r1 = fo[6];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        F[k] = fac1 * (r[k] * fac2 - r2 * aij[k]);
         ksum(b.v[3 * i + k], b.ve[3 * i + k], b.m[j] * F[k]);
         ksum(b.v[3 * j + k], b.ve[3 * j + k], -b.m[i] * F[k]);
       }
