@@ -16,11 +16,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "../../include/nbgrad.h"
-#include "nbg_jacobian.cuh"
+#include "nbg_jacobian_rx.cuh"
 
 using namespace nbg;
 
@@ -47,7 +48,7 @@ struct EventQueue {
   int32_t *sys, *step, *body, *k;
   double *dt0, *t;   // initial guess / time of the prior state
   double* snap;      // [12N][cap]  x, v, xe, ve
-  double* hdr;       // [8][cap]    dx, dy, dvx, dvy, gdot, vsky, dvdt, dt0_final  (written by transit_kernel)
+  double* hdr;       // [8][cap]    dx, dy, dvx, dvy, 1/gdot, 1/vsky, dvdt, dt0_final  (written by transit_kernel)
   double* stream;    // [step_fields][cap] operator stream of the final step
 };
 
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
     double* H = Q.hdr;
     const size_t cap = Q.cap;
     H[0 * cap + e] = dx; H[1 * cap + e] = dy; H[2 * cap + e] = dvx; H[3 * cap + e] = dvy;
-    H[4 * cap + e] = gd; H[5 * cap + e] = vsky; H[6 * cap + e] = dvdt; H[7 * cap + e] = dt0;
+    H[4 * cap + e] = 1.0 / gd; H[5 * cap + e] = 1.0 / vsky; H[6 * cap + e] = dvdt; H[7 * cap + e] = dt0;
   }
   if (st) atomicOr(&T.status[sys], st);
   atomicAdd(&counters[1], (unsigned long long)iter);
@@ -243,18 +244,18 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
         jac_apply_step(S, ev, n, M, c, 0.5 * dt0, tid, nthr);
         if (c < M) {
           const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
-          const double gd = Q.hdr[4 * cap + slot];
+          const double gdinv = Q.hdr[4 * cap + slot];
           const int j = i;  // occultor
           const double jx0 = S.Jv[(6 * j) * M + c] - S.Jv[(6 * ti) * M + c], jx1 = S.Jv[(6 * j + 1) * M + c] - S.Jv[(6 * ti + 1) * M + c];
           const double jv0 = S.Jv[(6 * j + 3) * M + c] - S.Jv[(6 * ti + 3) * M + c], jv1 = S.Jv[(6 * j + 4) * M + c] - S.Jv[(6 * ti + 4) * M + c];
-          const double dtdq = -(jx0 * dvx + jx1 * dvy + jv0 * dx + jv1 * dy) / gd;
+          const double dtdq = -(jx0 * dvx + jx1 * dvy + jv0 * dx + jv1 * dy) * gdinv;
           const size_t rec = (size_t)sys * O.RT + O.off[j] + Q.k[slot];
           if (O.C == 1) {
             O.dtdq0[rec * M + c] = dtdq;
           } else {
-            const double vsky = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
+            const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
             O.dtdq0[(rec * M + c) * 3] = dtdq;
-            O.dtdq0[(rec * M + c) * 3 + 1] = (jv0 * dvx + jv1 * dvy) / vsky + dvdt * dtdq;
+            O.dtdq0[(rec * M + c) * 3 + 1] = (jv0 * dvx + jv1 * dvy) * vskyinv + dvdt * dtdq;
             O.dtdq0[(rec * M + c) * 3 + 2] = 2.0 * (jx0 * dx + jx1 * dy);
           }
         }
@@ -266,6 +267,129 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   }
   __syncthreads();
   for (size_t q = tid; q < jsz; q += nthr) { Jv_g[sys * jsz + q] = S.Jv[q]; Je_g[sys * jsz + q] = S.Je[q]; }
+}
+
+// Register-resident Jacobian kernel (N <= 8): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
+// register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM
+template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 2 : (N == 5 ? 3 : 6); }
+
+template <int N>
+__global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
+    jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
+                  int nsteps, double h, const int32_t* __restrict__ evlist, EventQueue Q, int ti, TransitOut O) {
+  extern __shared__ __align__(16) double smrx[];
+  constexpr int M = 7 * N, P = N * (N - 1) / 2, SF = P * (2 * KF + PF), G = SF / 4, NT = rx_warps(N) * 32;
+  const long sys = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, c = warp * 16 + (lane & 15);
+  const bool valid = c < M;
+  RxState<N> S;
+#pragma unroll
+  for (int b = 0; b < N; ++b)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const size_t q = ((size_t)sys * 6 * N + 6 * b + 3 * half + k) * M + c;
+      S.jv[b][k] = valid ? Jv_g[q] : 0.0;
+      S.je[b][k] = valid ? Je_g[q] : 0.0;
+    }
+  double* const buf0 = smrx;
+  double* const buf1 = smrx + SF;
+  rx_fetch(buf0, stream, ld, (size_t)sys, G, tid, NT);
+  // One loop over work items -- a main step, or the extra step of a queued transit -- so that rx_step<N> (13k
+  // instructions, fully unrolled) exists once in the instruction stream.
+  double* const bk = Jbak + (size_t)sys * 6 * N * NT + tid;
+  const size_t cap = Q.cap;
+  int s = 0, ev_i = 0;
+  int32_t slot = -1;
+  bool in_event = false;
+  while (true) {
+    double* const cur = (s & 1) ? buf1 : buf0;
+    double h2;
+    if (!in_event) {
+      if (s >= nsteps) break;
+      __pipeline_wait_prior(0);
+      __syncthreads();  // step s operators visible; everyone is done with the other buffer
+      if (s + 1 < nsteps) rx_fetch((s & 1) ? buf0 : buf1, stream + (size_t)(s + 1) * SF * ld, ld, (size_t)sys, G, tid, NT);
+      h2 = 0.5 * h;
+    } else {
+      __syncthreads();  // everyone is done with cur
+      rx_fetch(cur, Q.stream, cap, (size_t)slot, G, tid, NT);
+      // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
+#pragma unroll
+      for (int b = 0; b < N; ++b)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { bk[(size_t)(3 * b + k) * NT] = S.jv[b][k]; bk[(size_t)(3 * N + 3 * b + k) * NT] = S.je[b][k]; }
+      __pipeline_wait_prior(0);
+      __syncthreads();
+      h2 = 0.5 * Q.hdr[7 * cap + slot];
+    }
+    rx_step<N>(S, cur, h2, half, c);
+    if (in_event) {
+      // dtbvdq! (timing.jl:155-194): rows x0,x1 (x half) and v0,v1 (v half) of occultor ev_i and transited body ti
+      double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+      for (int b = 0; b < N; ++b) {
+        const double sg = (b == ev_i ? 1.0 : 0.0) - (b == ti ? 1.0 : 0.0);
+        d0 = fma(sg, S.jv[b][0], d0);
+        d1 = fma(sg, S.jv[b][1], d1);
+      }
+      const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
+      const double gdinv = Q.hdr[4 * cap + slot];
+      const double mine = (half == 0) ? (d0 * dvx + d1 * dvy) : (d0 * dx + d1 * dy);
+      const double other = shx(mine);
+      const double dtdq = -(mine + other) * gdinv;  // meaningful in the x half
+      const size_t rec = (size_t)sys * O.RT + O.off[ev_i] + Q.k[slot];
+      if (O.C == 1) {
+        if (valid && half == 0) O.dtdq0[rec * M + c] = dtdq;
+      } else {
+        const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
+        const double s2 = shx(d0 * dvx + d1 * dvy);  // x half receives (jv0 dvx + jv1 dvy)
+        if (valid && half == 0) {
+          O.dtdq0[(rec * M + c) * 3] = dtdq;
+          O.dtdq0[(rec * M + c) * 3 + 1] = s2 * vskyinv + dvdt * dtdq;
+          O.dtdq0[(rec * M + c) * 3 + 2] = 2.0 * (d0 * dx + d1 * dy);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < N; ++b)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { S.jv[b][k] = bk[(size_t)(3 * b + k) * NT]; S.je[b][k] = bk[(size_t)(3 * N + 3 * b + k) * NT]; }
+    }
+    // next work item: remaining queued transits of step s, else step s + 1
+    ev_i = in_event ? ev_i + 1 : 0;
+    slot = -1;
+    if (evlist) {
+      for (; ev_i < N; ++ev_i) {
+        slot = evlist[((size_t)s * N + ev_i) * ld + sys];
+        if (slot >= 0) break;
+      }
+    }
+    in_event = slot >= 0;
+    if (!in_event) ++s;
+  }
+  if (valid) {
+#pragma unroll
+    for (int b = 0; b < N; ++b)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const size_t q = ((size_t)sys * 6 * N + 6 * b + 3 * half + k) * M + c;
+        Jv_g[q] = S.jv[b][k];
+        Je_g[q] = S.je[b][k];
+      }
+  }
+}
+
+template <int N>
+int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
+                  const int32_t* evlist, const EventQueue& Q, int ti, const TransitOut& O) {
+  constexpr int P = N * (N - 1) / 2, SF = P * (2 * KF + PF);
+  const size_t smem = (size_t)2 * SF * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(jac_rx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    attr_set = true;
+  }
+  jac_rx_kernel<N><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, Q, ti, O);
+  return 0;
 }
 
 // dtdelements = dtdq0 . jac_init  (calc_dtdelements!, timing.jl:112-138).  One block per (system, record tile).
@@ -390,7 +514,7 @@ struct nbg_plan {
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
   DevBuf stage[8];  // staging for host<->device conversions
-  bool has_state = false, jac_valid = false;
+  bool has_state = false, jac_valid = false, force_generic_jac = false;
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
@@ -493,15 +617,17 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     evlist = p->bevlist.as<int32_t>();
   }
   if (grad && detect) {
-    if (p->bJbak.ensure((size_t)nsys * 2 * jsz * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
+    const size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
+    if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
+  const bool use_rx = n <= 8 && !p->force_generic_jac;
   const int tpb = 128;
   const unsigned gridA = (unsigned)((nsys + tpb - 1) / tpb);
   const int tps = 32 * ((7 * n + 31) / 32);
   bool stage_phi = true;
   size_t smem = jac_smem_bytes(n, true);
   if (smem > 227 * 1024) { stage_phi = false; smem = jac_smem_bytes(n, false); }
-  if (grad) {
+  if (grad && !use_rx) {
     if (smem > 227 * 1024) return fail(NBG_ERR_UNSUPPORTED, "jac_step does not fit in shared memory for this nbody");
     CK(cudaFuncSetAttribute(jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -530,8 +656,25 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     }
     if (grad) {
       tm.begin(2);
-      jac_kernel<<<(unsigned)nsys, tps, smem, p->stream>>>(p->bJv.as<double>(), p->bJe.as<double>(), p->bJbak.as<double>(), n, ld,
-                                                          p->bstream.as<double>(), s, h, detect ? evlist : nullptr, Q, ti, O, stage_phi ? 1 : 0);
+      if (use_rx) {
+        const int32_t* evl = detect ? evlist : nullptr;
+        double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>(), *Jb = p->bJbak.as<double>();
+        const double* strm = p->bstream.as<double>();
+        int rc = 0;
+        switch (n) {
+          case 2: rc = launch_jac_rx<2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 3: rc = launch_jac_rx<3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 4: rc = launch_jac_rx<4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 5: rc = launch_jac_rx<5>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 6: rc = launch_jac_rx<6>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 7: rc = launch_jac_rx<7>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          default: rc = launch_jac_rx<8>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+        }
+        if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
+      } else {
+        jac_kernel<<<(unsigned)nsys, tps, smem, p->stream>>>(p->bJv.as<double>(), p->bJe.as<double>(), p->bJbak.as<double>(), n, ld,
+                                                            p->bstream.as<double>(), s, h, detect ? evlist : nullptr, Q, ti, O, stage_phi ? 1 : 0);
+      }
       tm.end();
       p->launches++;
     }
@@ -587,6 +730,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
     stream_budget_bytes = (int64_t)(fr / 4);
   }
   p->stream_budget = stream_budget_bytes;
+  if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   *out = p;

@@ -27,12 +27,12 @@ struct JacSmem {
   double* rec;  // [2][KF] staged Kepler record (double buffered)
 };
 
-// operator-stream reader: field f of this system/slot at base[f*stride + idx]
+// operator-stream reader: field f of this system/slot at ((f/4)*stride + idx)*4 + f%4  (see Emit)
 struct Src {
   const double* base;
   size_t stride;
   size_t idx;
-  __device__ __forceinline__ double get(size_t f) const { return __ldg(base + f * stride + idx); }
+  __device__ __forceinline__ double get(size_t f) const { return __ldg(base + ((f >> 2) * stride + idx) * 4 + (f & 3)); }
 };
 
 // Kahan fold of every stored entry of this thread's column: comp_sum_matrix! with a zero addend (utils.jl:36-46).
@@ -66,7 +66,7 @@ __device__ __forceinline__ void kepler_pair_column(const JacSmem& S, const doubl
   for (int r = 0; r < 6; ++r) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s += R[KF_K + 6 * r + k] * d[k];
+    for (int k = 0; k < 6; ++k) s += R[kf_k(r, k)] * d[k];
     w[r] = s;
   }
   const double mi = R[KF_MI], mj = R[KF_MJ];
@@ -75,11 +75,11 @@ __device__ __forceinline__ void kepler_pair_column(const JacSmem& S, const doubl
   for (int r = 0; r < 6; ++r) { ai[r] = mj * w[r]; aj[r] = -mi * w[r]; }
   if (c == 7 * i + 6) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { ai[r] += R[KF_CI7 + r]; aj[r] += R[KF_CJ7 + r]; }
+    for (int r = 0; r < 6; ++r) { ai[r] += R[kf_ci7(r)]; aj[r] += R[kf_cj7(r)]; }
   }
   if (c == 7 * j + 6) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) { ai[r] += R[KF_CI14 + r]; aj[r] += R[KF_CJ14 + r]; }
+    for (int r = 0; r < 6; ++r) { ai[r] += R[kf_ci14(r)]; aj[r] += R[kf_cj14(r)]; }
   }
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
@@ -107,12 +107,12 @@ __device__ __forceinline__ void phisalpha_column(const JacSmem& S, PhiGet PHI, i
     for (int k = 0; k < 3; ++k) xi[k] = S.Jv[(6 * i + k) * M + c];
     for (int j = i + 1; j < n; ++j, ++p) {
       const double r0 = PHI(p, PF_R), r1 = PHI(p, PF_R + 1), r2v = PHI(p, PF_R + 2);
-      const double g3 = PHI(p, PF_G3), r2 = PHI(p, PF_R2), mi = PHI(p, PF_MI), mj = PHI(p, PF_MJ);
+      const double g3 = PHI(p, PF_G3), mi = PHI(p, PF_MI), mj = PHI(p, PF_MJ);
       double w[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) w[k] = xi[k] - S.Jv[(6 * j + k) * M + c];
       const double rw = r0 * w[0] + r1 * w[1] + r2v * w[2];
-      const double f3 = 3.0 * g3 / r2 * rw;
+      const double f3 = PHI(p, PF_G5) * rw;
       double gw[3] = {g3 * w[0] - f3 * r0, g3 * w[1] - f3 * r1, g3 * w[2] - f3 * r2v};
       // mass columns: da_i -= gam_ij dm_j ; da_j += gam_ij dm_i     (gam = G r / r^3)
       const double dmj = (c == 7 * j + 6) ? 1.0 : 0.0, dmi = (c == 7 * i + 6) ? 1.0 : 0.0;

@@ -24,14 +24,18 @@ constexpr int NMAX = 16;  // max bodies per system
 constexpr int KF = 64;    // doubles per Kepler-pair operator record
 constexpr int PF = 24;    // doubles per phisalpha-pair operator record
 
-// Kepler record fields
-constexpr int KF_K = 0;      // 36: jac_kepler[r][c], r,c < 6  (index 6*r + c)
+// Kepler record fields.  The 6x6 block jac_kepler is stored as four 3x3 blocks ordered for the Jacobian kernel's
+// x-rows / v-rows thread halves: [Kxx, Kxv | Kvv, Kvx], then the mass-column terms split the same way.
+__host__ __device__ constexpr int kf_k(int r, int c) {  // jac_kepler[r][c], r,c < 6
+  return r < 3 ? (c < 3 ? 3 * r + c : 9 + 3 * r + (c - 3)) : (c >= 3 ? 18 + 3 * (r - 3) + (c - 3) : 27 + 3 * (r - 3) + c);
+}
 constexpr int KF_MI = 36;    // m_i/(m_i+m_j)
 constexpr int KF_MJ = 37;    // m_j/(m_i+m_j)
-constexpr int KF_CI7 = 38;   // 6: jac_ij[rows i][col m_i]
-constexpr int KF_CJ7 = 44;   // 6: jac_ij[rows j][col m_i]
-constexpr int KF_CI14 = 50;  // 6: jac_ij[rows i][col m_j]
-constexpr int KF_CJ14 = 56;  // 6: jac_ij[rows j][col m_j]
+// mass-column terms of jac_ij (ahl21.jl:743-750), row r < 6 of body i or j, column m_i ("7") or m_j ("14")
+__host__ __device__ constexpr int kf_ci7(int r) { return r < 3 ? 38 + r : 50 + (r - 3); }    // rows i, col m_i
+__host__ __device__ constexpr int kf_cj7(int r) { return r < 3 ? 41 + r : 53 + (r - 3); }    // rows j, col m_i
+__host__ __device__ constexpr int kf_ci14(int r) { return r < 3 ? 44 + r : 56 + (r - 3); }   // rows i, col m_j
+__host__ __device__ constexpr int kf_cj14(int r) { return r < 3 ? 47 + r : 59 + (r - 3); }   // rows j, col m_j
 // phisalpha record fields
 constexpr int PF_R = 0;      // 3: r_ij
 constexpr int PF_G3 = 3;     // G / r^3
@@ -42,6 +46,7 @@ constexpr int PF_RM = 7;     // 9: dF/dr [k][p]  (index 3*k + p)
 constexpr int PF_F = 16;     // 3: F_ij
 constexpr int PF_MI = 19;    // m_i
 constexpr int PF_MJ = 20;    // m_j
+constexpr int PF_G5 = 21;    // 3 G / r^5
 
 __host__ __device__ inline int npairs(int n) { return n * (n - 1) / 2; }
 // doubles per system per step in the operator stream
@@ -51,12 +56,13 @@ struct Body {
   double x[3 * NMAX], v[3 * NMAX], xe[3 * NMAX], ve[3 * NMAX], m[NMAX];
 };
 
-// Operator-stream writer: element (field f) of this thread's system/slot lives at base[f * stride + idx].
+// Operator-stream writer for this thread's system/slot (idx) out of `stride` systems/slots.
 struct Emit {
   double* base;
   size_t stride;
   size_t idx;
-  __device__ __forceinline__ void put(size_t f, double val) const { base[f * stride + idx] = val; }
+  // fields are packed in groups of 4 per system (32-byte sectors): element f at ((f/4)*stride + idx)*4 + f%4
+  __device__ __forceinline__ void put(size_t f, double val) const { base[((f >> 2) * stride + idx) * 4 + (f & 3)] = val; }
 };
 
 template <bool GRAD, bool EMIT>
@@ -110,15 +116,15 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) em.put(rec_base + KF_K + 6 * r + c, J.jk[r][c]);
+      for (int c = 0; c < 6; ++c) em.put(rec_base + kf_k(r, c), J.jk[r][c]);
     em.put(rec_base + KF_MI, mi);
     em.put(rec_base + KF_MJ, mj);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      em.put(rec_base + KF_CI7 + r, J.jm[r] * b.m[j]);
-      em.put(rec_base + KF_CJ7 + r, -mj * dl[r] * mijinv - kG * mi * J.jk[r][6]);
-      em.put(rec_base + KF_CI14 + r, mi * dl[r] * mijinv + kG * mj * J.jk[r][6]);
-      em.put(rec_base + KF_CJ14 + r, -J.jm[r] * b.m[i]);
+      em.put(rec_base + kf_ci7(r), J.jm[r] * b.m[j]);
+      em.put(rec_base + kf_cj7(r), -mj * dl[r] * mijinv - kG * mi * J.jk[r][6]);
+      em.put(rec_base + kf_ci14(r), mi * dl[r] * mijinv + kG * mj * J.jk[r][6]);
+      em.put(rec_base + kf_cj14(r), -J.jm[r] * b.m[i]);
     }
   }
 }
@@ -242,6 +248,7 @@ __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, do
             for (int q = 0; q < 3; ++q) em.put(rb + PF_RM + 3 * k + q, Rm[k][q]);
           em.put(rb + PF_MI, b.m[i]);
           em.put(rb + PF_MJ, b.m[j]);
+          em.put(rb + PF_G5, 3.0 * (kG / (r2 * r1)) / r2);
         }
       }
     }
