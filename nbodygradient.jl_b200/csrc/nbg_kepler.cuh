@@ -48,103 +48,72 @@ __device__ __forceinline__ double cubic1(double a, double b, double c) {
 }
 
 // ---- G3 / H-function series (utils.jl:137-165, 180-209, 225-254, 271-303, 320-349, 364-396) ----
-// Each is sum_n c_n x2^n with x2 = -sign(beta) gamma^2, terminated when the partial sum repeats.
-struct SeriesOut { double g3, h1, h2, h3, h5, h6; };
+// Each is sum_n c_n x2^n with x2 = -sign(beta) gamma^2.  The reference adds terms until the partial sum repeats; the
+// coefficients are fixed rationals, so for |gamma| < 0.5 the same sum is a short polynomial, evaluated here by Horner
+// with precomputed coefficients (no divisions, no data-dependent trip count; agrees with the term-by-term sum to ~1 ulp).
+// For |gamma| >= 0.5 the closed forms are used (the reference does so for gamma >= 0.5 and runs the slowly converging
+// series for gamma <= -0.5; both equal the closed form).
+#include "nbg_series_coeffs.inc"
+template <int NC> __device__ __forceinline__ double horner(const double (&c)[NC], double x) {
+  double s = c[0];
+#pragma unroll
+  for (int q = 1; q < NC; ++q) s = fma(s, x, c[q]);
+  return s;
+}
+__device__ __forceinline__ double series_g3(double x2) { constexpr double c[] = NBG_SER_G3; return horner(c, x2); }
+__device__ __forceinline__ double series_h1(double x2) { constexpr double c[] = NBG_SER_H1; return horner(c, x2); }
+__device__ __forceinline__ double series_h2(double x2) { constexpr double c[] = NBG_SER_H2; return horner(c, x2); }
+__device__ __forceinline__ double series_h3(double x2) { constexpr double c[] = NBG_SER_H3; return horner(c, x2); }
+__device__ __forceinline__ double series_h5(double x2) { constexpr double c[] = NBG_SER_H5; return horner(c, x2); }
+__device__ __forceinline__ double series_h6(double x2) { constexpr double c[] = NBG_SER_H6; return horner(c, x2); }
 
-__device__ __forceinline__ double series_g3(double x2) {
-  double term = 1.0, s = 1.0, s1 = 2.0, s2 = 2.0;
-  for (int n = 1; n <= 100; ++n) {
-    s2 = s1; s1 = s;
-    term *= x2 / (double)((2 * n + 3) * (2 * n + 2));
-    s += term;
-    if (s == s2 || s == s1) break;
+// sin/cos (elliptic) or sinh/cosh (hyperbolic) of the half-angle xx = gamma/2 (ahl21.jl:817-821, :836-840).
+// |xx| <= 0.5 (every step size an integrator would use): Taylor polynomials; otherwise libdevice.
+__device__ __forceinline__ void trig_pair(bool ell, double xx, double& sx, double& cx) {
+  if (fabs(xx) <= 0.5) {
+    constexpr double sc[] = NBG_SIN_C;
+    constexpr double cc[] = NBG_COS_C;
+    const double x2 = xx * xx;
+    // sin x = x + x^3 P(x^2), cos x = 1 + x^2 C(x^2); the hyperbolic series have the same coefficients with all signs
+    // positive, i.e. sinh x = x - x^3 P(-x^2), cosh x = 1 - x^2 C(-x^2)
+    const double y = ell ? x2 : -x2;
+    const double ps = horner(sc, y), pc = horner(cc, y);
+    sx = ell ? fma(xx * x2, ps, xx) : fma(-(xx * x2), ps, xx);
+    cx = ell ? fma(x2, pc, 1.0) : fma(-x2, pc, 1.0);
+  } else if (ell) {
+    sincos(xx, &sx, &cx);
+  } else {
+    sx = sinh(xx);
+    cx = exp(-xx) + sx;
   }
-  return s;
-}
-__device__ __forceinline__ double series_h1(double x2) {
-  double term = 1.0, s = 1.0, s1 = 2.0, s2 = 2.0;
-  for (int n = 1; n <= 100; ++n) {
-    s2 = s1; s1 = s;
-    term *= x2 * (double)(n + 1);
-    term /= (double)((2 * n + 4) * (2 * n + 3) * n);
-    s += term;
-    if (s == s2 || s == s1) break;
-  }
-  return s;
-}
-__device__ __forceinline__ double series_h2(double x2) {
-  double term = 1.0, s = 1.0, s1 = 2.0, s2 = 2.0;
-  for (int n = 1; n <= 100; ++n) {
-    s2 = s1; s1 = s;
-    term *= x2;
-    term /= (double)((4 * n + 6) * n);
-    s += term;
-    if (s == s2 || s == s1) break;
-  }
-  return s;
-}
-__device__ __forceinline__ double series_h3(double x2) {
-  double term = 1.0 / 30.0, s = 1.0 / 10.0, s1 = 2.0 * s, s2 = s1, four2n = 4.0;
-  for (int n = 1; n <= 100; ++n) {
-    s2 = s1; s1 = s;
-    term *= x2;
-    term /= (double)((2 * n + 4) * (2 * n + 5));
-    four2n *= 4.0;
-    s += term * (four2n - 1.0);
-    if (s == s2 || s == s1) break;
-  }
-  return s;
-}
-__device__ __forceinline__ double series_h5(double x2) {
-  double term = 1.0 / 60.0, s = term, s1 = 2.0 * s, s2 = s1;
-  for (int n = 1; n <= 100; ++n) {
-    s2 = s1; s1 = s;
-    term *= x2 * (double)(n + 1);
-    term /= (double)((2 * n + 5) * (2 * n + 4) * n);
-    s += term;
-    if (s == s2 || s == s1) break;
-  }
-  return s;
-}
-__device__ __forceinline__ double series_h6(double x2) {
-  double term = 1.0 / 360.0, s = 1.0 / 40.0, s1 = 2.0 * s, s2 = s1, four2n = 16.0;
-  for (int n = 1; n <= 100; ++n) {
-    s2 = s1; s1 = s;
-    term *= x2;
-    term /= (double)((2 * n + 5) * (2 * n + 6));
-    four2n *= 4.0;
-    s += term * (four2n - (double)(3 * n) - 7.0);
-    if (s == s2 || s == s1) break;
-  }
-  return s;
 }
 
 __device__ __forceinline__ double G3f(double gamma, double beta, double sqb) {
-  if (gamma < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_g3(x2) * (-x2 * gamma / (6.0 * beta * sqb)); }
+  if (fabs(gamma) < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_g3(x2) * (-x2 * gamma / (6.0 * beta * sqb)); }
   return (beta >= 0.0) ? (gamma - sin(gamma)) / (sqb * beta) : (gamma - sinh(gamma)) / (sqb * beta);
 }
 __device__ __forceinline__ double H1f(double gamma, double beta) {
-  if (gamma < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h1(x2) * ((x2 * x2) / (12.0 * (beta * beta))); }
+  if (fabs(gamma) < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h1(x2) * ((x2 * x2) / (12.0 * (beta * beta))); }
   if (beta >= 0.0) { double s = sin(0.5 * gamma); return (4.0 * (s * s) - gamma * sin(gamma)) / (beta * beta); }
   double s = sinh(0.5 * gamma);
   return (-4.0 * (s * s) + gamma * sinh(gamma)) / (beta * beta);
 }
 __device__ __forceinline__ double H2f(double gamma, double beta, double sqb) {
-  if (gamma < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h2(x2) * (-x2 * gamma / (3.0 * beta * sqb)); }
+  if (fabs(gamma) < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h2(x2) * (-x2 * gamma / (3.0 * beta * sqb)); }
   return (beta >= 0.0) ? (sin(gamma) - gamma * cos(gamma)) / (sqb * beta) : (sinh(gamma) - gamma * cosh(gamma)) / (sqb * beta);
 }
 __device__ __forceinline__ double H3f(double gamma, double beta, double sqb) {
-  if (gamma < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h3(x2) * (-(x2 * x2) * gamma / (beta * sqb)); }
+  if (fabs(gamma) < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h3(x2) * (-(x2 * x2) * gamma / (beta * sqb)); }
   return (beta >= 0.0) ? (4.0 * sin(gamma) - sin(gamma) * cos(gamma) - 3.0 * gamma) / (beta * sqb)
                        : (4.0 * sinh(gamma) - sinh(gamma) * cosh(gamma) - 3.0 * gamma) / (beta * sqb);
 }
 __device__ __forceinline__ double H5f(double gamma, double beta, double sqb) {
-  if (gamma < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h5(x2) * (-(x2 * x2) * gamma / (beta * sqb)); }
+  if (fabs(gamma) < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h5(x2) * (-(x2 * x2) * gamma / (beta * sqb)); }
   return (beta >= 0.0) ? (3.0 * sin(gamma) - 2.0 * gamma - gamma * cos(gamma)) / (beta * sqb)
                        : (3.0 * sinh(gamma) - 2.0 * gamma - gamma * cosh(gamma)) / (beta * sqb);
 }
 __device__ __forceinline__ double H6f(double gamma, double beta) {
-  if (gamma < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h6(x2) * (-(x2 * x2 * x2) / (beta * beta)); }
+  if (fabs(gamma) < 0.5) { double x2 = -sgn(beta) * (gamma * gamma); return series_h6(x2) * (-(x2 * x2 * x2) / (beta * beta)); }
   return (beta >= 0.0) ? (9.0 - 8.0 * cos(gamma) - cos(2.0 * gamma) - 6.0 * gamma * sin(gamma)) / (2.0 * (beta * beta))
                        : (9.0 - 8.0 * cosh(gamma) - cosh(2.0 * gamma) + 6.0 * gamma * sinh(gamma)) / (2.0 * (beta * beta));
 }
@@ -188,17 +157,11 @@ __device__ __noinline__ void kepler_solve(const double* __restrict__ x0, const d
   for (int iter = 0; iter < 20; ++iter) {
     gamma2 = gamma1;
     gamma1 = gamma;
-    double xx = 0.5 * gamma;
-    if (ell) sincos(xx, &sx, &cx);
-    else { sx = sinh(xx); cx = exp(-xx) + sx; }
+    trig_pair(ell, 0.5 * gamma, sx, cx);
     gamma -= (k * gamma + c2n * sx * cx + c3n * (sx * sx) + c4n) / (d1 * (sx * sx) + c3n * sx * cx + d3);
     if (gamma == gamma2 || gamma == gamma1) break;
   }
-  {
-    double xx = 0.5 * gamma;
-    if (ell) sincos(xx, &sx, &cx);
-    else { sx = sinh(xx); cx = exp(-xx) + sx; }
-  }
+  trig_pair(ell, 0.5 * gamma, sx, cx);
   const double g1 = 2.0 * sx * cx / sqb;
   const double g2 = 2.0 * signb * (sx * sx) * betainv;
   const double g0 = 1.0 - beta * g2;

@@ -63,6 +63,15 @@ struct Emit {
   size_t idx;
   // fields are packed in groups of 4 per system (32-byte sectors): element f at ((f/4)*stride + idx)*4 + f%4
   __device__ __forceinline__ void put(size_t f, double val) const { base[((f >> 2) * stride + idx) * 4 + (f & 3)] = val; }
+  // a whole record of NF (multiple of 4) doubles starting at field f0 (multiple of 4), as 16-byte stores
+  template <int NF> __device__ __forceinline__ void put_record(size_t f0, const double (&rec)[NF]) const {
+#pragma unroll
+    for (int g = 0; g < NF / 4; ++g) {
+      double2* dst = reinterpret_cast<double2*>(base + (((f0 >> 2) + g) * stride + idx) * 4);
+      dst[0] = make_double2(rec[4 * g], rec[4 * g + 1]);
+      dst[1] = make_double2(rec[4 * g + 2], rec[4 * g + 3]);
+    }
+  }
 };
 
 template <bool GRAD, bool EMIT>
@@ -76,7 +85,12 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
   if (gm == 0.0) {
     // Two massless bodies: no interaction.  (The reference returns before touching anything, ahl21.jl:713,
     // and then re-applies the previous pair's stale jac_ij; here the pair is the identity.)
-    if (EMIT) for (int f = 0; f < KF; ++f) em.put(rec_base + f, 0.0);
+    if (EMIT) {
+      double rec[KF];
+#pragma unroll
+      for (int f = 0; f < KF; ++f) rec[f] = 0.0;
+      em.put_record<KF>(rec_base, rec);
+    }
     return;
   }
   KepScal P;
@@ -113,19 +127,22 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
     }
   }
   if (EMIT) {
+    double rec[KF];
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) em.put(rec_base + kf_k(r, c), J.jk[r][c]);
-    em.put(rec_base + KF_MI, mi);
-    em.put(rec_base + KF_MJ, mj);
+      for (int c = 0; c < 6; ++c) rec[kf_k(r, c)] = J.jk[r][c];
+    rec[KF_MI] = mi;
+    rec[KF_MJ] = mj;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      em.put(rec_base + kf_ci7(r), J.jm[r] * b.m[j]);
-      em.put(rec_base + kf_cj7(r), -mj * dl[r] * mijinv - kG * mi * J.jk[r][6]);
-      em.put(rec_base + kf_ci14(r), mi * dl[r] * mijinv + kG * mj * J.jk[r][6]);
-      em.put(rec_base + kf_cj14(r), -J.jm[r] * b.m[i]);
+      rec[kf_ci7(r)] = J.jm[r] * b.m[j];
+      rec[kf_cj7(r)] = -mj * dl[r] * mijinv - kG * mi * J.jk[r][6];
+      rec[kf_ci14(r)] = mi * dl[r] * mijinv + kG * mj * J.jk[r][6];
+      rec[kf_cj14(r)] = -J.jm[r] * b.m[i];
     }
+    rec[62] = 0.0; rec[63] = 0.0;
+    em.put_record<KF>(rec_base, rec);
   }
 }
 
@@ -235,20 +252,23 @@ __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, do
           }
         }
         if (EMIT) {
-          const size_t rb = rec_base + (size_t)p * PF;
+          double rec[PF];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) { em.put(rb + PF_R + k, r[k]); em.put(rb + PF_F + k, F[k]); }
-          em.put(rb + PF_G3, kG / (r2 * r1));
-          em.put(rb + PF_FAC1, fac1);
-          em.put(rb + PF_R2, r2);
-          em.put(rb + PF_US, 2.0 * kG * fac1 / r1);
+          for (int k = 0; k < 3; ++k) { rec[PF_R + k] = r[k]; rec[PF_F + k] = F[k]; }
+          const double g3 = kG / (r2 * r1);
+          rec[PF_G3] = g3;
+          rec[PF_FAC1] = fac1;
+          rec[PF_R2] = r2;
+          rec[PF_US] = 2.0 * kG * fac1 / r1;
 #pragma unroll
           for (int k = 0; k < 3; ++k)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) em.put(rb + PF_RM + 3 * k + q, Rm[k][q]);
-          em.put(rb + PF_MI, b.m[i]);
-          em.put(rb + PF_MJ, b.m[j]);
-          em.put(rb + PF_G5, 3.0 * (kG / (r2 * r1)) / r2);
+            for (int q = 0; q < 3; ++q) rec[PF_RM + 3 * k + q] = Rm[k][q];
+          rec[PF_MI] = b.m[i];
+          rec[PF_MJ] = b.m[j];
+          rec[PF_G5] = 3.0 * g3 * r2inv;
+          rec[22] = 0.0; rec[23] = 0.0;
+          em.put_record<PF>(rec_base + (size_t)p * PF, rec);
         }
       }
     }
