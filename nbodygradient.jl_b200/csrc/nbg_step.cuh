@@ -74,12 +74,37 @@ struct Emit {
   }
 };
 
+// One body's state held in registers while it takes part in a run of pair updates.  Body arrays live in thread-local
+// memory with run-time indices; ncu (profiles/r01_t2_traj) showed >50% of the trajectory kernel's stall samples waiting
+// on those dependent local loads at the top of every pair.  The sweeps therefore keep body i in registers across its
+// whole j loop and fetch body j+1 while pair (i, j) is being solved.
+struct BodyRegs {
+  double x[3], v[3], xe[3], ve[3], m, dq[6];
+};
+template <bool GRAD> __device__ __forceinline__ void load_body(const Body& b, const double* dq, int i, BodyRegs& r) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { r.x[k] = b.x[3 * i + k]; r.v[k] = b.v[3 * i + k]; r.xe[k] = b.xe[3 * i + k]; r.ve[k] = b.ve[3 * i + k]; }
+  r.m = b.m[i];
+  if (GRAD) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r.dq[k] = dq[6 * i + k];
+  }
+}
+template <bool GRAD> __device__ __forceinline__ void store_body(Body& b, double* dq, int i, const BodyRegs& r) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { b.x[3 * i + k] = r.x[k]; b.v[3 * i + k] = r.v[k]; b.xe[3 * i + k] = r.xe[k]; b.ve[3 * i + k] = r.ve[k]; }
+  if (GRAD) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dq[6 * i + k] = r.dq[k];
+  }
+}
+
 template <bool GRAD, bool EMIT>
-__device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, double h2, bool drift_first, const Emit& em, size_t rec_base) {
+__device__ __forceinline__ void pair_section(BodyRegs& bi, BodyRegs& bj, double h2, bool drift_first, const Emit& em, size_t rec_base) {
   double x0[3], v0[3], dl[6];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { x0[k] = b.x[3 * i + k] - b.x[3 * j + k]; v0[k] = b.v[3 * i + k] - b.v[3 * j + k]; }
-  const double msum = b.m[i] + b.m[j];
+  for (int k = 0; k < 3; ++k) { x0[k] = bi.x[k] - bj.x[k]; v0[k] = bi.v[k] - bj.v[k]; }
+  const double msum = bi.m + bj.m;
   const double gm = kG * msum;
   KepJac J;
   if (gm == 0.0) {
@@ -97,22 +122,22 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
   kepler_solve(x0, v0, gm, h2, drift_first, dl, &P);
   if (GRAD) kepler_jacobian(&P, x0, v0, drift_first, &J);
   const double mijinv = 1.0 / msum;
-  const double mi = b.m[i] * mijinv, mj = b.m[j] * mijinv;
+  const double mi = bi.m * mijinv, mj = bj.m * mijinv;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ksum(b.x[3 * i + k], b.xe[3 * i + k], mj * dl[k]);
-    ksum(b.x[3 * j + k], b.xe[3 * j + k], -mi * dl[k]);
+    ksum(bi.x[k], bi.xe[k], mj * dl[k]);
+    ksum(bj.x[k], bj.xe[k], -mi * dl[k]);
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ksum(b.v[3 * i + k], b.ve[3 * i + k], mj * dl[3 + k]);
-    ksum(b.v[3 * j + k], b.ve[3 * j + k], -mi * dl[3 + k]);
+    ksum(bi.v[k], bi.ve[k], mj * dl[3 + k]);
+    ksum(bj.v[k], bj.ve[k], -mi * dl[3 + k]);
   }
   if (GRAD) {
     // dqdt_ij = dqdt_ij/2 + dqdt_old + jac_ij * dqdt_old   (ahl21.jl:38-40); mass entries of dqdt are identically 0
     double dd[6], w[6];
 #pragma unroll
-    for (int l = 0; l < 6; ++l) dd[l] = dq[6 * i + l] - dq[6 * j + l];
+    for (int l = 0; l < 6; ++l) dd[l] = bi.dq[l] - bj.dq[l];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       double s = 0.0;
@@ -122,8 +147,8 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      dq[6 * i + r] = 0.5 * (mj * J.jk[r][7]) + dq[6 * i + r] + mj * w[r];
-      dq[6 * j + r] = 0.5 * (-mi * J.jk[r][7]) + dq[6 * j + r] - mi * w[r];
+      bi.dq[r] = 0.5 * (mj * J.jk[r][7]) + bi.dq[r] + mj * w[r];
+      bj.dq[r] = 0.5 * (-mi * J.jk[r][7]) + bj.dq[r] - mi * w[r];
     }
   }
   if (EMIT) {
@@ -136,10 +161,10 @@ __device__ __forceinline__ void pair_section(Body& b, double* dq, int i, int j, 
     rec[KF_MJ] = mj;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      rec[kf_ci7(r)] = J.jm[r] * b.m[j];
+      rec[kf_ci7(r)] = J.jm[r] * bj.m;
       rec[kf_cj7(r)] = -mj * dl[r] * mijinv - kG * mi * J.jk[r][6];
       rec[kf_ci14(r)] = mi * dl[r] * mijinv + kG * mj * J.jk[r][6];
-      rec[kf_cj14(r)] = -J.jm[r] * b.m[i];
+      rec[kf_cj14(r)] = -J.jm[r] * bi.m;
     }
     rec[62] = 0.0; rec[63] = 0.0;
     em.put_record<KF>(rec_base, rec);
@@ -292,11 +317,31 @@ __device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em)
     }
   }
   int rec = 0;
-  for (int i = 0; i < n - 1; ++i)
-    for (int j = i + 1; j < n; ++j, ++rec) pair_section<GRAD, EMIT>(b, dq, i, j, h2, true, em, (size_t)rec * KF);
+  for (int i = 0; i < n - 1; ++i) {
+    BodyRegs bi, bj, bn;
+    load_body<GRAD>(b, dq, i, bi);
+    load_body<GRAD>(b, dq, i + 1, bn);
+    for (int j = i + 1; j < n; ++j, ++rec) {
+      bj = bn;
+      if (j + 1 < n) load_body<GRAD>(b, dq, j + 1, bn);  // in flight while pair (i, j) is solved
+      pair_section<GRAD, EMIT>(bi, bj, h2, true, em, (size_t)rec * KF);
+      store_body<GRAD>(b, dq, j, bj);
+    }
+    store_body<GRAD>(b, dq, i, bi);
+  }
   phisalpha_section<GRAD, EMIT>(b, dq, n, h, em, (size_t)2 * P * KF);
-  for (int i = n - 2; i >= 0; --i)
-    for (int j = n - 1; j >= i + 1; --j, ++rec) pair_section<GRAD, EMIT>(b, dq, i, j, h2, false, em, (size_t)rec * KF);
+  for (int i = n - 2; i >= 0; --i) {
+    BodyRegs bi, bj, bn;
+    load_body<GRAD>(b, dq, i, bi);
+    load_body<GRAD>(b, dq, n - 1, bn);
+    for (int j = n - 1; j >= i + 1; --j, ++rec) {
+      bj = bn;
+      if (j - 1 >= i + 1) load_body<GRAD>(b, dq, j - 1, bn);
+      pair_section<GRAD, EMIT>(bi, bj, h2, false, em, (size_t)rec * KF);
+      store_body<GRAD>(b, dq, j, bj);
+    }
+    store_body<GRAD>(b, dq, i, bi);
+  }
   for (int i = 0; i < n; ++i) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
