@@ -271,9 +271,9 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 
 // Register-resident Jacobian kernel (N <= 8): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
 // register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM
-template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 2 : (N == 5 ? 3 : 6); }
+template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
-template <int N>
+template <int N, int U>
 __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
                   int nsteps, double h, const int32_t* __restrict__ evlist, EventQueue Q, int ti, TransitOut O) {
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
       __syncthreads();
       h2 = 0.5 * Q.hdr[7 * cap + slot];
     }
-    rx_step<N>(S, cur, h2, half, c);
+    rx_step<N, U>(S, cur, h2, half, c);
     if (in_event) {
       // dtbvdq! (timing.jl:155-194): rows x0,x1 (x half) and v0,v1 (v half) of occultor ev_i and transited body ti
       double d0 = 0.0, d1 = 0.0;
@@ -378,17 +378,18 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
   }
 }
 
-template <int N>
+template <int N, int U>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
                   const int32_t* evlist, const EventQueue& Q, int ti, const TransitOut& O) {
   constexpr int P = N * (N - 1) / 2, SF = P * (2 * KF + PF);
   const size_t smem = (size_t)2 * SF * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(jac_rx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(jac_rx_kernel<N, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(jac_rx_kernel<N, U>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
-  jac_rx_kernel<N><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, Q, ti, O);
+  jac_rx_kernel<N, U><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, Q, ti, O);
   return 0;
 }
 
@@ -515,6 +516,7 @@ struct nbg_plan {
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
   DevBuf stage[8];  // staging for host<->device conversions
   bool has_state = false, jac_valid = false, force_generic_jac = false;
+  int rx_unroll = 2;
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
@@ -662,13 +664,17 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         const double* strm = p->bstream.as<double>();
         int rc = 0;
         switch (n) {
-          case 2: rc = launch_jac_rx<2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 3: rc = launch_jac_rx<3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 4: rc = launch_jac_rx<4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 5: rc = launch_jac_rx<5>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 6: rc = launch_jac_rx<6>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 7: rc = launch_jac_rx<7>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          default: rc = launch_jac_rx<8>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 2: rc = launch_jac_rx<2, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 3: rc = launch_jac_rx<3, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 4: rc = launch_jac_rx<4, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 5: rc = launch_jac_rx<5, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 6: rc = launch_jac_rx<6, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 7: rc = launch_jac_rx<7, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          default:
+            if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O);
+            else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O);
+            else rc = launch_jac_rx<8, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O);
+            break;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
       } else {
@@ -731,6 +737,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   }
   p->stream_budget = stream_budget_bytes;
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
+  if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
   if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   *out = p;

@@ -58,37 +58,37 @@ __device__ __forceinline__ void rx_fetch(double* dst, const double* base, size_t
 // arrays are indexed by POSITION and rotated by one position between groups of pairs, so that the body being paired
 // with all later bodies always sits at position 0: the code holds N-1 pair bodies per sweep instead of N(N-1)/2, and
 // the group loop is a real loop.  A rotation is 3N (or 6N) register moves, issued in the shadow of the FP64 pipe.
-template <int N> __device__ __forceinline__ void rot_left(double (&a)[N][3]) {
-  const double t0 = a[0][0], t1 = a[0][1], t2 = a[0][2];
+template <int N, int K> __device__ __forceinline__ void rot_left_by(double (&a)[N][3]) {  // position p <- position p + K (mod N)
+  constexpr int KK = ((K % N) + N) % N;
+  if constexpr (KK != 0) {
+    double t[N][3];
 #pragma unroll
-  for (int p = 0; p < N - 1; ++p) { a[p][0] = a[p + 1][0]; a[p][1] = a[p + 1][1]; a[p][2] = a[p + 1][2]; }
-  a[N - 1][0] = t0; a[N - 1][1] = t1; a[N - 1][2] = t2;
-}
-template <int N> __device__ __forceinline__ void rot_right(double (&a)[N][3]) {
-  const double t0 = a[N - 1][0], t1 = a[N - 1][1], t2 = a[N - 1][2];
+    for (int p = 0; p < N; ++p) { t[p][0] = a[(p + KK) % N][0]; t[p][1] = a[(p + KK) % N][1]; t[p][2] = a[(p + KK) % N][2]; }
 #pragma unroll
-  for (int p = N - 1; p > 0; --p) { a[p][0] = a[p - 1][0]; a[p][1] = a[p - 1][1]; a[p][2] = a[p - 1][2]; }
-  a[0][0] = t0; a[0][1] = t1; a[0][2] = t2;
+    for (int p = 0; p < N; ++p) { a[p][0] = t[p][0]; a[p][1] = t[p][1]; a[p][2] = t[p][2]; }
+  }
 }
 
-// pair update between positions 0 and T; ci/cj = mass columns (7*body+6) of the bodies at those positions
-template <int N, int T>
+// pair update between positions PA and PB; ci/cj = mass columns (7*body+6) of the bodies at those positions
+template <int N, int PA, int PB>
 __device__ __forceinline__ void rx_pair(RxState<N>& S, const double* __restrict__ R, int half, int c, int ci, int cj) {
   double md[3], od[3], w[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) md[k] = S.jv[0][k] - S.jv[T][k];
+  for (int k = 0; k < 3; ++k) md[k] = S.jv[PA][k] - S.jv[PB][k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) od[k] = shx(md[k]);
   const double* __restrict__ Kb = R + 18 * half;  // [A (3x3) | B (3x3)] of this half
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
+    // two 3-term chains (own half / partner half) instead of one 6-term chain: shorter dependent latency; the
+    // partner-half chain also waits on the shuffle, the own-half chain does not
     double s = Kb[3 * k] * md[0];
     s = fma(Kb[3 * k + 1], md[1], s);
     s = fma(Kb[3 * k + 2], md[2], s);
-    s = fma(Kb[9 + 3 * k], od[0], s);
-    s = fma(Kb[9 + 3 * k + 1], od[1], s);
-    s = fma(Kb[9 + 3 * k + 2], od[2], s);
-    w[k] = s;
+    double u = Kb[9 + 3 * k] * od[0];
+    u = fma(Kb[9 + 3 * k + 1], od[1], u);
+    u = fma(Kb[9 + 3 * k + 2], od[2], u);
+    w[k] = s + u;
   }
   const double2 mm = *reinterpret_cast<const double2*>(R + KF_MI);
   double ai[3], aj[3];
@@ -101,26 +101,9 @@ __device__ __forceinline__ void rx_pair(RxState<N>& S, const double* __restrict_
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ksum_m(S.jv[0][k], S.je[0][k], ai[k]);
-    ksum_m(S.jv[T][k], S.je[T][k], aj[k]);
+    ksum_m(S.jv[PA][k], S.je[PA][k], ai[k]);
+    ksum_m(S.jv[PB][k], S.je[PB][k], aj[k]);
   }
-}
-
-// group of the ascending sweep: body g (position 0) with bodies g+1 .. N-1 (positions 1 .. N-1-g), ascending
-template <int N> __device__ __forceinline__ void rx_group_asc(RxState<N>& S, const double* __restrict__ R, int g, int half, int c) {
-  const int tmax = N - 1 - g;
-  static_for<1, N>([&](auto Tc) {
-    constexpr int T = decltype(Tc)::value;
-    if (T <= tmax) rx_pair<N, T>(S, R + (T - 1) * KF, half, c, 7 * g + 6, 7 * (g + T) + 6);
-  });
-}
-// group of the descending sweep: body i (position 0) with bodies N-1 .. i+1 (positions N-1-i .. 1), descending
-template <int N> __device__ __forceinline__ void rx_group_desc(RxState<N>& S, const double* __restrict__ R, int i, int half, int c) {
-  const int tmax = N - 1 - i;
-  static_for<1, N>([&](auto Uc) {
-    constexpr int T = N - decltype(Uc)::value;  // N-1 down to 1
-    if (T <= tmax) rx_pair<N, T>(S, R + (tmax - T) * KF, half, c, 7 * i + 6, 7 * (i + T) + 6);
-  });
 }
 
 template <int N> __device__ __forceinline__ void rx_drift(RxState<N>& S, double h2, int half) {
@@ -142,13 +125,13 @@ template <int N> __device__ __forceinline__ void rx_fold(RxState<N>& S) {
 // phisalpha Jacobian in factored form (see nbg_step.cuh).  The x half computes; the v half's aux registers hold the
 // per-body da accumulators during pass 1/2, the x half's aux registers hold the dv accumulators during pass 2.
 // Pass 1, positions 0 and T: x half forms Gam_ij (dx_i - dx_j) (+ mass term) and ships it; v half accumulates da.
-template <int N, int T>
+template <int N, int PA, int PB>
 __device__ __forceinline__ void rx_phi1(const RxState<N>& S, double (&aux)[N][3], const double* __restrict__ R, int half, int c, int ci, int cj) {
   const double r0 = R[PF_R], r1 = R[PF_R + 1], r2v = R[PF_R + 2], g3 = R[PF_G3];
   const double mi = R[PF_MI], mj = R[PF_MJ];
   double w[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) w[k] = S.jv[0][k] - S.jv[T][k];
+  for (int k = 0; k < 3; ++k) w[k] = S.jv[PA][k] - S.jv[PB][k];
   const double rw = r0 * w[0] + r1 * w[1] + r2v * w[2];
   const double f3 = R[PF_G5] * rw;
   const double dmj = (c == cj) ? 1.0 : 0.0, dmi = (c == ci) ? 1.0 : 0.0;
@@ -159,17 +142,17 @@ __device__ __forceinline__ void rx_phi1(const RxState<N>& S, double (&aux)[N][3]
     const double ga = g3 * rr[k];
     const double ti_ = shx(mj * gw + ga * dmj);  // contribution to -da_i
     const double tj_ = shx(mi * gw + ga * dmi);  // contribution to +da_j
-    if (half == 1) { aux[0][k] -= ti_; aux[T][k] += tj_; }
+    if (half == 1) { aux[PA][k] -= ti_; aux[PB][k] += tj_; }
   }
 }
 // Pass 2, positions 0 and T: v half ships da_i - da_j, x half forms dF and accumulates dv in its aux.
-template <int N, int T>
+template <int N, int PA, int PB>
 __device__ __forceinline__ void rx_phi2(const RxState<N>& S, double (&aux)[N][3], const double* __restrict__ R, int half, int c, int ci, int cj) {
   const double r0 = R[PF_R], r1 = R[PF_R + 1], r2v = R[PF_R + 2], fac1 = R[PF_FAC1], r2 = R[PF_R2], us = R[PF_US];
   const double mi = R[PF_MI], mj = R[PF_MJ];
   double w[3], wa[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { w[k] = S.jv[0][k] - S.jv[T][k]; wa[k] = shx(aux[0][k] - aux[T][k]); }
+  for (int k = 0; k < 3; ++k) { w[k] = S.jv[PA][k] - S.jv[PB][k]; wa[k] = shx(aux[PA][k] - aux[PB][k]); }
   if (half == 0) {
     const double rwa = r0 * wa[0] + r1 * wa[1] + r2v * wa[2];
     const double dmi = (c == ci) ? 1.0 : 0.0, dmj = (c == cj) ? 1.0 : 0.0;
@@ -179,42 +162,82 @@ __device__ __forceinline__ void rx_phi2(const RxState<N>& S, double (&aux)[N][3]
       const double dF = R[PF_RM + 3 * k] * w[0] + R[PF_RM + 3 * k + 1] * w[1] + R[PF_RM + 3 * k + 2] * w[2] +
                         fac1 * (3.0 * rr[k] * rwa - r2 * wa[k]) + us * rr[k] * (dmi + dmj);
       const double F = R[PF_F + k];
-      aux[0][k] += mj * dF + F * dmj;
-      aux[T][k] -= mi * dF + F * dmi;
+      aux[PA][k] += mj * dF + F * dmj;
+      aux[PB][k] -= mi * dF + F * dmi;
     }
   }
 }
 
-// On entry and exit the arrangement is "rotated left by N-1" ([N-1, 0, 1, ..., N-2]); each pass makes N left rotations.
-template <int N> __device__ __forceinline__ void rx_phisalpha(RxState<N>& S, const double* __restrict__ PH, int half, int c) {
+// ---- sweeps over pairs in blocks of U pivot bodies ---------------------------------------------------------------
+// "offset r" = position p holds body (r + p) mod N.  A block of U consecutive pivots runs with the lowest pivot at
+// position 0 (pivot u at static position u, its partner at static position u + T); between blocks the arrays rotate by U.
+// U = 1 minimises code, U = N is the full unroll; U trades register moves against instruction-cache footprint.
+template <int N, int U, bool SYNC = true> struct RxSweep {
+  static constexpr int NB = (N - 1 + U - 1) / U;      // blocks covering pivots 0 .. N-2
+  static constexpr int A1 = (NB * U) % N;             // offset after an ascending pass
+  static constexpr int KTOP = (N - 2) / U;            // top block of the descending sweep
+  // ascending pairs (i < j in the reference order); F(PA, PB, record pointer, body_i, body_j)
+  template <class Arr, class F> static __device__ __forceinline__ void asc(Arr&& rotate, const double* R, int stride, F&& f) {
+#pragma unroll 1
+    for (int g0 = 0; g0 < N - 1; g0 += U) {
+      static_for<0, U>([&](auto Uc) {
+        constexpr int u = decltype(Uc)::value;
+        const int g = g0 + u;
+        if (g < N - 1) {
+          const int tmax = N - 1 - g;
+          static_for<1, N - u>([&](auto Tc) {
+            constexpr int T = decltype(Tc)::value;
+            if (T <= tmax) f(std::integral_constant<int, u>{}, std::integral_constant<int, u + T>{}, R + (T - 1) * stride, g, g + T);
+          });
+          R += tmax * stride;
+        }
+      });
+      rotate(std::integral_constant<int, U>{});
+      // keep the warps of the block within one group of each other: the instruction stream is long and straight, and
+      // warps at unrelated program counters thrash the instruction cache (ncu r01_rx4: no_instruction 1.0 per issue)
+      if (SYNC) __syncthreads();
+    }
+  }
+  // descending pairs (i = N-2 .. 0, j = N-1 .. i+1); entered at offset KTOP*U, leaves at offset 0
+  template <class Arr, class F> static __device__ __forceinline__ void desc(Arr&& rotate, const double* R, int stride, F&& f) {
+#pragma unroll 1
+    for (int kb = KTOP; kb >= 0; --kb) {
+      static_for<0, U>([&](auto Uc) {
+        constexpr int u = U - 1 - decltype(Uc)::value;  // U-1 down to 0
+        const int i = kb * U + u;
+        if (i <= N - 2) {
+          const int tmax = N - 1 - i;
+          static_for<1, N - u>([&](auto Vc) {
+            constexpr int T = N - u - decltype(Vc)::value;  // N-1-u down to 1
+            if (T <= tmax) f(std::integral_constant<int, u>{}, std::integral_constant<int, u + T>{}, R + (tmax - T) * stride, i, i + T);
+          });
+          R += tmax * stride;
+        }
+      });
+      if (kb > 0) rotate(std::integral_constant<int, -U>{});
+      if (SYNC) __syncthreads();
+    }
+  }
+};
+
+// phisalpha: jv and aux enter at offset A1 (je stays there throughout), leave at offset A1
+template <int N, int U> __device__ __forceinline__ void rx_phisalpha(RxState<N>& S, const double* __restrict__ PH, int half, int c) {
+  using SW = RxSweep<N, U>;
   double aux[N][3];
 #pragma unroll
   for (int b = 0; b < N; ++b)
 #pragma unroll
     for (int k = 0; k < 3; ++k) aux[b][k] = 0.0;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const double* R = PH;
-#pragma unroll 1
-    for (int g = 0; g < N; ++g) {
-      rot_left<N>(S.jv);
-      rot_left<N>(aux);
-      const int tmax = N - 1 - g;
-      if (pass == 0) {
-        static_for<1, N>([&](auto Tc) {
-          constexpr int T = decltype(Tc)::value;
-          if (T <= tmax) rx_phi1<N, T>(S, aux, R + (T - 1) * PF, half, c, 7 * g + 6, 7 * (g + T) + 6);
-        });
-      } else {
-        static_for<1, N>([&](auto Tc) {
-          constexpr int T = decltype(Tc)::value;
-          if (T <= tmax) rx_phi2<N, T>(S, aux, R + (T - 1) * PF, half, c, 7 * g + 6, 7 * (g + T) + 6);
-        });
-      }
-      R += tmax * PF;
-    }
-  }
-  // arrangement is [N-1, 0, ..., N-2] again, for jv, je (never moved) and aux alike
+  auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(aux); };
+  rotate(std::integral_constant<int, N - SW::A1>{});  // to offset 0
+  SW::asc(rotate, PH, PF, [&](auto PA, auto PB, const double* R, int bi, int bj) {
+    rx_phi1<N, decltype(PA)::value, decltype(PB)::value>(S, aux, R, half, c, 7 * bi + 6, 7 * bj + 6);
+  });
+  rotate(std::integral_constant<int, N - SW::A1>{});
+  SW::asc(rotate, PH, PF, [&](auto PA, auto PB, const double* R, int bi, int bj) {
+    rx_phi2<N, decltype(PA)::value, decltype(PB)::value>(S, aux, R, half, c, 7 * bi + 6, 7 * bj + 6);
+  });
+  // jv, je, aux all at offset A1
   // comp_sum_matrix!(jac_step, jac_error, jac_phi * jac_step): v rows get dv, x rows a zero addend (fold)
 #pragma unroll
   for (int b = 0; b < N; ++b)
@@ -225,32 +248,20 @@ template <int N> __device__ __forceinline__ void rx_phisalpha(RxState<N>& S, con
     }
 }
 
-// one AHL21 Jacobian step from a staged operator block; arrangement is the identity on entry and exit
-template <int N> __device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c) {
+// one AHL21 Jacobian step from a staged operator block; offset 0 (identity) on entry and exit
+template <int N, int U> __device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c) {
   constexpr int P = N * (N - 1) / 2;
+  using SW = RxSweep<N, U>;
+  auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(S.je); };
+  auto pair = [&](auto PA, auto PB, const double* R, int bi, int bj) {
+    rx_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, half, c, 7 * bi + 6, 7 * bj + 6);
+  };
   rx_drift<N>(S, h2, half);
   rx_fold<N>(S);
-  {
-    const double* R = blk;
-#pragma unroll 1
-    for (int g = 0; g < N - 1; ++g) {
-      rx_group_asc<N>(S, R, g, half, c);
-      R += (N - 1 - g) * KF;
-      rot_left<N>(S.jv);
-      rot_left<N>(S.je);
-    }
-  }
-  rx_phisalpha<N>(S, blk + 2 * P * KF, half, c);
-  {
-    const double* R = blk + P * KF;
-#pragma unroll 1
-    for (int i = N - 2; i >= 0; --i) {
-      rot_right<N>(S.jv);
-      rot_right<N>(S.je);
-      rx_group_desc<N>(S, R, i, half, c);
-      R += (N - 1 - i) * KF;
-    }
-  }
+  SW::asc(rotate, blk, KF, pair);                                          // offset 0 -> A1
+  rx_phisalpha<N, U>(S, blk + 2 * P * KF, half, c);                        // A1 -> A1
+  rotate(std::integral_constant<int, SW::KTOP * U - SW::A1>{});            // A1 -> KTOP*U
+  SW::desc(rotate, blk + P * KF, KF, pair);                                // -> 0
   rx_drift<N>(S, h2, half);
   rx_fold<N>(S);
 }
