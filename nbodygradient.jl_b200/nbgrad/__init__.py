@@ -4,6 +4,7 @@ from .ics import (Elements, ElementsIC, CartesianIC, get_default_ICs, available_
                   trappist1_elements, GNEWT, YEAR)
 from .integrator import State, dState, Integrator, TransitTiming, TransitParameters, ahl21, check_step, device_count, release_plans
 from ._lib import NbgError, lib, SYMBOLS
+from .sharding import shard_range, shard_counts, max_over_ranks, sum_over_ranks, gather_slices
 
 __all__ = ["Elements", "ElementsIC", "CartesianIC", "get_default_ICs", "available_systems", "State", "dState", "Integrator", "TransitTiming",
            "TransitParameters", "ahl21", "NbgError"]
