@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
       __syncthreads();
       h2 = 0.5 * Q.hdr[7 * cap + slot];
     }
-    rx_step<N, U>(S, cur, h2, half, c);
+    rx_step<N, U>(S, cur, RxPhi<N>::ALIAS ? cur : smrx + 2 * SF, h2, half, c, tid, NT);
     if (in_event) {
       // dtbvdq! (timing.jl:155-194): rows x0,x1 (x half) and v0,v1 (v half) of occultor ev_i and transited body ti
       double d0 = 0.0, d1 = 0.0;
@@ -382,7 +382,7 @@ template <int N, int U>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
                   const int32_t* evlist, const EventQueue& Q, int ti, const TransitOut& O) {
   constexpr int P = N * (N - 1) / 2, SF = P * (2 * KF + PF);
-  const size_t smem = (size_t)2 * SF * 8;
+  const size_t smem = ((size_t)2 * SF + (RxPhi<N>::ALIAS ? 0 : RxPhi<N>::SIZE)) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(jac_rx_kernel<N, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;

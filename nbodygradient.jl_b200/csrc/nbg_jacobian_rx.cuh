@@ -122,50 +122,148 @@ template <int N> __device__ __forceinline__ void rx_fold(RxState<N>& S) {
     for (int k = 0; k < 3; ++k) ksum_m(S.jv[b][k], S.je[b][k], 0.0);
 }
 
-// phisalpha Jacobian in factored form (see nbg_step.cuh).  The x half computes; the v half's aux registers hold the
-// per-body da accumulators during pass 1/2, the x half's aux registers hold the dv accumulators during pass 2.
-// Pass 1, positions 0 and T: x half forms Gam_ij (dx_i - dx_j) (+ mass term) and ships it; v half accumulates da.
-template <int N, int PA, int PB>
-__device__ __forceinline__ void rx_phi1(const RxState<N>& S, double (&aux)[N][3], const double* __restrict__ R, int half, int c, int ci, int cj) {
-  const double r0 = R[PF_R], r1 = R[PF_R + 1], r2v = R[PF_R + 2], g3 = R[PF_G3];
-  const double mi = R[PF_MI], mj = R[PF_MJ];
-  double w[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) w[k] = S.jv[PA][k] - S.jv[PB][k];
-  const double rw = r0 * w[0] + r1 * w[1] + r2v * w[2];
-  const double f3 = R[PF_G5] * rw;
-  const double dmj = (c == cj) ? 1.0 : 0.0, dmi = (c == ci) ? 1.0 : 0.0;
-  const double rr[3] = {r0, r1, r2v};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double gw = g3 * w[k] - f3 * rr[k];
-    const double ga = g3 * rr[k];
-    const double ti_ = shx(mj * gw + ga * dmj);  // contribution to -da_i
-    const double tj_ = shx(mi * gw + ga * dmi);  // contribution to +da_j
-    if (half == 1) { aux[PA][k] -= ti_; aux[PB][k] += tj_; }
-  }
-}
-// Pass 2, positions 0 and T: v half ships da_i - da_j, x half forms dF and accumulates dv in its aux.
-template <int N, int PA, int PB>
-__device__ __forceinline__ void rx_phi2(const RxState<N>& S, double (&aux)[N][3], const double* __restrict__ R, int half, int c, int ci, int cj) {
-  const double r0 = R[PF_R], r1 = R[PF_R + 1], r2v = R[PF_R + 2], fac1 = R[PF_FAC1], r2 = R[PF_R2], us = R[PF_US];
-  const double mi = R[PF_MI], mj = R[PF_MJ];
-  double w[3], wa[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { w[k] = S.jv[PA][k] - S.jv[PB][k]; wa[k] = shx(aux[PA][k] - aux[PB][k]); }
-  if (half == 0) {
-    const double rwa = r0 * wa[0] + r1 * wa[1] + r2v * wa[2];
-    const double dmi = (c == ci) ? 1.0 : 0.0, dmj = (c == cj) ? 1.0 : 0.0;
-    const double rr[3] = {r0, r1, r2v};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double dF = R[PF_RM + 3 * k] * w[0] + R[PF_RM + 3 * k + 1] * w[1] + R[PF_RM + 3 * k + 2] * w[2] +
-                        fac1 * (3.0 * rr[k] * rwa - r2 * wa[k]) + us * rr[k] * (dmi + dmj);
-      const double F = R[PF_F + k];
-      aux[PA][k] += mj * dF + F * dmj;
-      aux[PB][k] -= mi * dF + F * dmi;
+// ---- phisalpha as a DENSE operator -----------------------------------------------------------------------------
+// jac_phi (ahl21.jl:635-693) is nonzero only in its v rows x {x, m} columns.  Applying it pair by pair in factored form
+// costs ~85 FP64 instructions per pair and thread (r01 profile: 45% of the kernel's FP64 issue for 5% of the canonical
+// flops); as a dense 3N x 3N block it is 9N^2/2 DFMA per thread.  The trajectory kernel still streams the compact
+// per-pair records (PF doubles); the block assembles the dense blocks cooperatively in shared memory once per step:
+//   a_i = - sum_d G m_d r_id / r^3,   T_p = G (I/r^3 - 3 r r^T / r^5),   S_p = fac1 (3 r r^T - r^2 I)      (p = pair)
+//   Ax[i][d] = m_d T_id (d != i),  Ax[i][i] = - sum_l Ax[i][l];   Am[i][d] = - G r_id / r^3 (d != i),  Am[i][i] = 0
+//   Phi_x[i][d] = sum_{j != i} m_j S_ij (Ax[i][d] - Ax[j][d])  +  (d == i ? sum_j m_j Rm_ij : - m_d Rm_id)
+//   Phi_m[i][d] = sum_{j != i} m_j S_ij (Am[i][d] - Am[j][d])  +  (d == i ? sum_j m_j us_ij r_ij : m_d us_id r_id + F_id)
+// with r_ij, F_ij oriented from body i (sign flips for i > j); same linear operator as the reference's jac_phi.
+template <int N> struct RxPhi {
+  static constexpr int NA = (N + 1) / 2;        // bodies whose x rows the x half multiplies; the v half takes the rest
+  static constexpr int KIN = 3 * NA;            // inputs per half (zero padded when N is odd)
+  static constexpr int PHX = 0;                 // [half][3N rows][KIN]
+  static constexpr int PHM = PHX + 2 * 3 * N * KIN;  // [3N rows][N]
+  static constexpr int AX = PHM + 3 * N * N;    // [i][d][6]  symmetric 3x3: xx xy xz yy yz zz
+  static constexpr int AM = AX + 6 * N * N;     // [i][d][3]
+  static constexpr int SIZE = AM + 3 * N * N;   // doubles of scratch
+  static constexpr bool ALIAS = SIZE <= (N * (N - 1) / 2) * KF;  // fits in the (dead) ascending-sweep records of the current buffer
+};
+__device__ __forceinline__ int rx_pair_index(int n, int a, int b) { return a * n - a * (a + 1) / 2 + (b - a - 1); }  // a < b
+
+template <int N> __device__ __forceinline__ void rx_phi_assemble(const double* __restrict__ PH, double* __restrict__ W, int tid, int nthr) {
+  using L = RxPhi<N>;
+  // stage A: off-diagonal blocks of Ax, Am
+  for (int t = tid; t < N * N; t += nthr) {
+    const int i = t / N, d = t % N;
+    if (i != d) {
+      const double* R = PH + rx_pair_index(N, i < d ? i : d, i < d ? d : i) * PF;
+      const double sg = i < d ? 1.0 : -1.0;
+      const double r0 = R[PF_R], r1 = R[PF_R + 1], r2 = R[PF_R + 2], g3 = R[PF_G3], g5 = R[PF_G5];
+      const double md = i < d ? R[PF_MJ] : R[PF_MI];
+      double* a = W + L::AX + 6 * t;
+      a[0] = md * (g3 - g5 * r0 * r0); a[1] = md * (-g5 * r0 * r1); a[2] = md * (-g5 * r0 * r2);
+      a[3] = md * (g3 - g5 * r1 * r1); a[4] = md * (-g5 * r1 * r2); a[5] = md * (g3 - g5 * r2 * r2);
+      double* am = W + L::AM + 3 * t;
+      am[0] = -sg * g3 * r0; am[1] = -sg * g3 * r1; am[2] = -sg * g3 * r2;
+    } else {
+      double* am = W + L::AM + 3 * t;
+      am[0] = 0.0; am[1] = 0.0; am[2] = 0.0;
     }
   }
+  if (N & 1)  // zero padding of the v half's unused inputs
+    for (int t = tid; t < 3 * N * 3; t += nthr) W[L::PHX + (3 * N + t / 3) * L::KIN + (L::KIN - 3) + t % 3] = 0.0;
+  __syncthreads();
+  // stage B: diagonal blocks
+  for (int t = tid; t < 6 * N; t += nthr) {
+    const int i = t / 6, q = t % 6;
+    double s = 0.0;
+    for (int l = 0; l < N; ++l)
+      if (l != i) s -= W[L::AX + 6 * (i * N + l) + q];
+    W[L::AX + 6 * (i * N + i) + q] = s;
+  }
+  __syncthreads();
+  // stage C: one task per (i, d, input column): p < 3 an x column of body d, p == 3 its mass column
+  for (int t = tid; t < N * N * 4; t += nthr) {
+    const int p = t & 3, d = (t >> 2) % N, i = (t >> 2) / N;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const double* R = PH + rx_pair_index(N, i < j ? i : j, i < j ? j : i) * PF;
+      const double sg = i < j ? 1.0 : -1.0;
+      const double mj = i < j ? R[PF_MJ] : R[PF_MI];
+      const double r0 = R[PF_R], r1 = R[PF_R + 1], r2 = R[PF_R + 2], fac1 = R[PF_FAC1], rsq = R[PF_R2];
+      double u0, u1, u2;  // column p of A[i][d] - A[j][d]
+      if (p < 3) {
+        const double* ai = W + L::AX + 6 * (i * N + d);
+        const double* aj = W + L::AX + 6 * (j * N + d);
+        // symmetric storage: column p of [0 1 2; 1 3 4; 2 4 5]
+        const int q0 = p, q1 = p == 0 ? 1 : (p == 1 ? 3 : 4), q2 = p == 0 ? 2 : (p == 1 ? 4 : 5);
+        u0 = ai[q0] - aj[q0]; u1 = ai[q1] - aj[q1]; u2 = ai[q2] - aj[q2];
+      } else {
+        const double* ai = W + L::AM + 3 * (i * N + d);
+        const double* aj = W + L::AM + 3 * (j * N + d);
+        u0 = ai[0] - aj[0]; u1 = ai[1] - aj[1]; u2 = ai[2] - aj[2];
+      }
+      const double ru = 3.0 * (r0 * u0 + r1 * u1 + r2 * u2);
+      double e0 = fac1 * (r0 * ru - rsq * u0), e1 = fac1 * (r1 * ru - rsq * u1), e2 = fac1 * (r2 * ru - rsq * u2);
+      if (p < 3) {
+        if (d == i) { e0 += R[PF_RM + p]; e1 += R[PF_RM + 3 + p]; e2 += R[PF_RM + 6 + p]; }
+        else if (d == j) { e0 -= R[PF_RM + p]; e1 -= R[PF_RM + 3 + p]; e2 -= R[PF_RM + 6 + p]; }
+        acc0 = fma(mj, e0, acc0); acc1 = fma(mj, e1, acc1); acc2 = fma(mj, e2, acc2);
+      } else {
+        if (d == i || d == j) { const double us = sg * R[PF_US]; e0 = fma(us, r0, e0); e1 = fma(us, r1, e1); e2 = fma(us, r2, e2); }
+        acc0 = fma(mj, e0, acc0); acc1 = fma(mj, e1, acc1); acc2 = fma(mj, e2, acc2);
+        if (d == j) { acc0 = fma(sg, R[PF_F], acc0); acc1 = fma(sg, R[PF_F + 1], acc1); acc2 = fma(sg, R[PF_F + 2], acc2); }
+      }
+    }
+    if (p < 3) {
+      const int hf = d >= L::NA ? 1 : 0, col = 3 * (d - hf * L::NA) + p;
+      double* o = W + L::PHX + (hf * 3 * N + 3 * i) * L::KIN + col;
+      o[0] = acc0; o[L::KIN] = acc1; o[2 * L::KIN] = acc2;
+    } else {
+      double* o = W + L::PHM + (3 * i) * N + d;
+      o[0] = acc0; o[N] = acc1; o[2 * N] = acc2;
+    }
+  }
+  __syncthreads();
+}
+
+// jac_step (+)= jac_phi * jac_step with the dense blocks of rx_phi_assemble; jv/je at offset OFF (position p holds
+// body (OFF + p) mod N).  Each half multiplies its KIN inputs into all 3N outputs, the v half adds the two partial sums.
+template <int N, int OFF> __device__ __forceinline__ void rx_phisalpha_dense(RxState<N>& S, const double* __restrict__ W, int half, int c) {
+  using L = RxPhi<N>;
+  double in[L::KIN];
+  static_for<0, L::NA>([&](auto Qc) {
+    constexpr int q = decltype(Qc)::value;
+    constexpr int pa = (q - OFF + 2 * N) % N;              // position of body q (x half's input)
+    constexpr int bb = L::NA + q;                          // body whose x rows the v half receives
+    if constexpr (bb < N) {
+      constexpr int pb = (bb - OFF + 2 * N) % N;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double got = shx(S.jv[pb][k]);
+        in[3 * q + k] = half ? got : S.jv[pa][k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) in[3 * q + k] = half ? 0.0 : S.jv[pa][k];
+    }
+  });
+  // mass column of body dm (or -1): the v half adds Phi_m[:, dm]
+  const int dm = (c % 7 == 6 && c < 7 * N) ? c / 7 : -1;
+  const double* __restrict__ Wh = W + L::PHX + half * 3 * N * L::KIN;
+  static_for<0, N>([&](auto Bc) {
+    constexpr int b = decltype(Bc)::value;
+    constexpr int pos = (b - OFF + 2 * N) % N;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double* __restrict__ row = Wh + (3 * b + k) * L::KIN;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int t = 0; t + 1 < L::KIN; t += 2) { s0 = fma(row[t], in[t], s0); s1 = fma(row[t + 1], in[t + 1], s1); }
+      if (L::KIN & 1) s0 = fma(row[L::KIN - 1], in[L::KIN - 1], s0);
+      double part = s0 + s1;
+      const double other = shx(part);
+      double dv = part + other;
+      if (dm >= 0) dv += W[L::PHM + (3 * b + k) * N + dm];
+      // comp_sum_matrix!(jac_step, jac_error, jac_phi * jac_step): v rows get dv, x rows a zero addend (fold)
+      ksum_m(S.jv[pos][k], S.je[pos][k], half == 1 ? dv : 0.0);
+    }
+  });
 }
 
 // ---- sweeps over pairs in blocks of U pivot bodies ---------------------------------------------------------------
@@ -220,36 +318,10 @@ template <int N, int U, bool SYNC = true> struct RxSweep {
   }
 };
 
-// phisalpha: jv and aux enter at offset A1 (je stays there throughout), leave at offset A1
-template <int N, int U> __device__ __forceinline__ void rx_phisalpha(RxState<N>& S, const double* __restrict__ PH, int half, int c) {
-  using SW = RxSweep<N, U>;
-  double aux[N][3];
-#pragma unroll
-  for (int b = 0; b < N; ++b)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) aux[b][k] = 0.0;
-  auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(aux); };
-  rotate(std::integral_constant<int, N - SW::A1>{});  // to offset 0
-  SW::asc(rotate, PH, PF, [&](auto PA, auto PB, const double* R, int bi, int bj) {
-    rx_phi1<N, decltype(PA)::value, decltype(PB)::value>(S, aux, R, half, c, 7 * bi + 6, 7 * bj + 6);
-  });
-  rotate(std::integral_constant<int, N - SW::A1>{});
-  SW::asc(rotate, PH, PF, [&](auto PA, auto PB, const double* R, int bi, int bj) {
-    rx_phi2<N, decltype(PA)::value, decltype(PB)::value>(S, aux, R, half, c, 7 * bi + 6, 7 * bj + 6);
-  });
-  // jv, je, aux all at offset A1
-  // comp_sum_matrix!(jac_step, jac_error, jac_phi * jac_step): v rows get dv, x rows a zero addend (fold)
-#pragma unroll
-  for (int b = 0; b < N; ++b)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double dv = shx(aux[b][k]);  // v half receives the x half's accumulator
-      ksum_m(S.jv[b][k], S.je[b][k], half == 1 ? dv : 0.0);
-    }
-}
-
-// one AHL21 Jacobian step from a staged operator block; offset 0 (identity) on entry and exit
-template <int N, int U> __device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c) {
+// one AHL21 Jacobian step from a staged operator block; offset 0 (identity) on entry and exit.
+// scr: scratch for the dense phisalpha blocks (the block's own ascending records when RxPhi<N>::ALIAS).
+template <int N, int U>
+__device__ __forceinline__ void rx_step(RxState<N>& S, double* __restrict__ blk, double* __restrict__ scr, double h2, int half, int c, int tid, int nthr) {
   constexpr int P = N * (N - 1) / 2;
   using SW = RxSweep<N, U>;
   auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(S.je); };
@@ -258,8 +330,9 @@ template <int N, int U> __device__ __forceinline__ void rx_step(RxState<N>& S, c
   };
   rx_drift<N>(S, h2, half);
   rx_fold<N>(S);
-  SW::asc(rotate, blk, KF, pair);                                          // offset 0 -> A1
-  rx_phisalpha<N, U>(S, blk + 2 * P * KF, half, c);                        // A1 -> A1
+  SW::asc(rotate, blk, KF, pair);                                          // offset 0 -> A1; ends with a block barrier
+  rx_phi_assemble<N>(blk + 2 * P * KF, scr, tid, nthr);
+  rx_phisalpha_dense<N, SW::A1>(S, scr, half, c);                          // A1 -> A1
   rotate(std::integral_constant<int, SW::KTOP * U - SW::A1>{});            // A1 -> KTOP*U
   SW::desc(rotate, blk + P * KF, KF, pair);                                // -> 0
   rx_drift<N>(S, h2, half);
