@@ -111,10 +111,11 @@ int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, c
  *  c[0] main-loop system-steps, c[1] findtransit Newton step-equivalents, c[2] final (Jacobian) transit steps,
  *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main + transit).
  * nbg_last_timings: device milliseconds (CUDA events on the plan's stream) spent in the last compute call in the
- *  trajectory kernel [0], transit-refinement kernel [1], Jacobian kernel [2], everything else [3]; [4] = total. */
+ *  trajectory kernel [0], transit-refinement kernel [1], Jacobian kernel [2], everything else [3]; [4] = total;
+ *  [5] = dense phisalpha-operator kernel; [6], [7] reserved (0). */
 int32_t nbg_counters(nbg_plan* plan, int64_t* c8);
 int32_t nbg_counters_reset(nbg_plan* plan);
-int32_t nbg_last_timings(nbg_plan* plan, double* ms5);
+int32_t nbg_last_timings(nbg_plan* plan, double* ms8);
 int64_t nbg_cuda_stream(nbg_plan* plan); /* cudaStream_t of the plan, for callers that time with their own events */
 /* FP64 (DFMA) pipe peak of `device`, measured with 8 independent FMA chains per thread: the roofline denominator
  * for this path (the driver-written MEASURED_PEAKS.json carries HBM and bf16 figures only). */

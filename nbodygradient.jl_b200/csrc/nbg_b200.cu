@@ -64,7 +64,7 @@ struct TransitOut {
 template <bool GRAD, bool EMIT>
 __global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, int detect, int ti,
                                                    double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
-                                                   int32_t* evlist, int time_mode_kahan, double* tkahan_err) {
+                                                   int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err) {
   const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= nsys) return;
   const size_t ld = T.ld;
@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsy
     if (time_mode_kahan) ksum(tnow, terr, h);                      // (intr)(s,N): Integrator.jl:229
     else tnow = t0 + ((double)(istep0 + s + 1) * h);               // Transits.jl:161
     if (detect) {
+      uint32_t mask = 0;
       for (int i = 0; i < n; ++i) {
         int32_t slot = -1;
         if (i != ti) {
@@ -117,7 +118,9 @@ __global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsy
           gs[i] = gi;
         }
         if (evlist) evlist[((size_t)s * n + i) * ld + sys] = slot;
+        if (slot >= 0) mask |= 1u << i;
       }
+      if (evmask) evmask[(size_t)s * ld + sys] = mask;
     }
   }
   bool finite = true;
@@ -273,12 +276,13 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 // register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
-template <int N, int U>
-__global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>()>
+__global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
-                  int nsteps, double h, const int32_t* __restrict__ evlist, EventQueue Q, int ti, TransitOut O) {
+                  int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O) {
   extern __shared__ __align__(16) double smrx[];
-  constexpr int M = 7 * N, P = N * (N - 1) / 2, SF = P * (2 * KF + PF), G = SF / 4, NT = rx_warps(N) * 32;
+  constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + PF) + 12 * N * N /* stream */, SB = 2 * P * KF + 12 * N * N /* staged */,
+                G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = rx_warps(N) * 32;
   const long sys = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, c = warp * 16 + (lane & 15);
   const bool valid = c < M;
@@ -292,27 +296,29 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
       S.je[b][k] = valid ? Je_g[q] : 0.0;
     }
   double* const buf0 = smrx;
-  double* const buf1 = smrx + SF;
-  rx_fetch(buf0, stream, ld, (size_t)sys, G, tid, NT);
+  double* const buf1 = smrx + SB;
+  rx_fetch(buf0, stream, ld, (size_t)sys, G0, GSKIP, G1, tid, NT);
   // One loop over work items -- a main step, or the extra step of a queued transit -- so that rx_step<N> (13k
   // instructions, fully unrolled) exists once in the instruction stream.
   double* const bk = Jbak + (size_t)sys * 6 * N * NT + tid;
   const size_t cap = Q.cap;
   int s = 0, ev_i = 0;
   int32_t slot = -1;
+  uint32_t pend = 0;  // bodies with a queued transit at the end of step s (read at the start of the step, used at its end)
   bool in_event = false;
   while (true) {
     double* const cur = (s & 1) ? buf1 : buf0;
     double h2;
     if (!in_event) {
       if (s >= nsteps) break;
+      pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
       __pipeline_wait_prior(0);
       __syncthreads();  // step s operators visible; everyone is done with the other buffer
-      if (s + 1 < nsteps) rx_fetch((s & 1) ? buf0 : buf1, stream + (size_t)(s + 1) * SF * ld, ld, (size_t)sys, G, tid, NT);
+      if (s + 1 < nsteps) rx_fetch((s & 1) ? buf0 : buf1, stream + (size_t)(s + 1) * SFS * ld, ld, (size_t)sys, G0, GSKIP, G1, tid, NT);
       h2 = 0.5 * h;
     } else {
       __syncthreads();  // everyone is done with cur
-      rx_fetch(cur, Q.stream, cap, (size_t)slot, G, tid, NT);
+      rx_fetch(cur, Q.stream, cap, (size_t)slot, G0, GSKIP, G1, tid, NT);
       // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
 #pragma unroll
       for (int b = 0; b < N; ++b)
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
       __syncthreads();
       h2 = 0.5 * Q.hdr[7 * cap + slot];
     }
-    rx_step<N, U>(S, cur, RxPhi<N>::ALIAS ? cur : smrx + 2 * SF, h2, half, c, tid, NT);
+    rx_step<N, U, SYNC>(S, cur, h2, half, c);
     if (in_event) {
       // dtbvdq! (timing.jl:155-194): rows x0,x1 (x half) and v0,v1 (v half) of occultor ev_i and transited body ti
       double d0 = 0.0, d1 = 0.0;
@@ -355,16 +361,14 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
         for (int k = 0; k < 3; ++k) { S.jv[b][k] = bk[(size_t)(3 * b + k) * NT]; S.je[b][k] = bk[(size_t)(3 * N + 3 * b + k) * NT]; }
     }
     // next work item: remaining queued transits of step s, else step s + 1
-    ev_i = in_event ? ev_i + 1 : 0;
-    slot = -1;
-    if (evlist) {
-      for (; ev_i < N; ++ev_i) {
-        slot = evlist[((size_t)s * N + ev_i) * ld + sys];
-        if (slot >= 0) break;
-      }
+    in_event = pend != 0u;
+    if (in_event) {
+      ev_i = __ffs(pend) - 1;
+      pend &= pend - 1u;
+      slot = evlist[((size_t)s * N + ev_i) * ld + sys];
+    } else {
+      ++s;
     }
-    in_event = slot >= 0;
-    if (!in_event) ++s;
   }
   if (valid) {
 #pragma unroll
@@ -378,18 +382,45 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, rx_minblocks<N>())
   }
 }
 
-template <int N, int U>
+// Dense phisalpha operator (see nbg_jacobian_rx.cuh): one thread per (system or queued transit, step, body i); the 32
+// lanes of a warp are consecutive systems, so every record read and every output write is a coalesced run of sectors.
+template <int N>
+__global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(double* __restrict__ base, size_t stride, long nitems, const int32_t* __restrict__ nitems_dev,
+                                                           size_t step_elems) {
+  const long idx = (long)blockIdx.x * 32 + threadIdx.x;
+  const long nv = nitems_dev ? min((long)*nitems_dev, nitems) : nitems;
+  if (idx >= nv) return;
+  phi_dense_rows<N>(base + (size_t)blockIdx.y * step_elems, stride, (size_t)idx, (int)threadIdx.y);
+}
+int launch_phi_dense(cudaStream_t st, int n, double* base, size_t stride, long nitems, const int32_t* nitems_dev, int nsteps) {
+  if (nitems <= 0 || nsteps <= 0) return 0;
+  const dim3 grid((unsigned)((nitems + 31) / 32), (unsigned)nsteps), block(32, n);
+  const size_t se = step_fields(n) * stride;
+  switch (n) {
+    case 2: phi_dense_kernel<2><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 3: phi_dense_kernel<3><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 4: phi_dense_kernel<4><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 5: phi_dense_kernel<5><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 6: phi_dense_kernel<6><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 7: phi_dense_kernel<7><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 8: phi_dense_kernel<8><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>()>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
-                  const int32_t* evlist, const EventQueue& Q, int ti, const TransitOut& O) {
-  constexpr int P = N * (N - 1) / 2, SF = P * (2 * KF + PF);
-  const size_t smem = ((size_t)2 * SF + (RxPhi<N>::ALIAS ? 0 : RxPhi<N>::SIZE)) * 8;
+                  const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O) {
+  constexpr int P = N * (N - 1) / 2, SB = 2 * P * KF + 12 * N * N;
+  const size_t smem = (size_t)2 * SB * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(jac_rx_kernel<N, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(jac_rx_kernel<N, U>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
-  jac_rx_kernel<N, U><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, Q, ti, O);
+  jac_rx_kernel<N, U, SYNC, MB><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O);
   return 0;
 }
 
@@ -511,7 +542,7 @@ struct nbg_plan {
   cudaStream_t stream = nullptr;
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
-  DevBuf bJv, bJe, bJbak, bstream, bevlist;
+  DevBuf bJv, bJe, bJbak, bstream, bevlist, bevmask;
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
   DevBuf stage[8];  // staging for host<->device conversions
@@ -521,7 +552,7 @@ struct nbg_plan {
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
   unsigned long long counters_host[8] = {0};
-  double timings[5] = {0, 0, 0, 0, 0};
+  double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
 };
 
@@ -600,6 +631,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   EventQueue Q{};
   TransitOut O{};
   int32_t* evlist = nullptr;
+  uint32_t* evmask = nullptr;
   if (detect) {
     double rate = std::min<double>(n - 1, rate_hint * 2.0 + 0.05);
     long cap = (long)std::ceil((double)nsys * (double)S * rate) + 4096;
@@ -612,11 +644,13 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     bad |= p->qhdr.ensure((size_t)8 * cap * 8);
     if (grad) bad |= p->qstream.ensure(sf * (size_t)cap * 8);
     bad |= p->bevlist.ensure((size_t)S * n * ld * 4);
+    bad |= p->bevmask.ensure((size_t)S * ld * 4);
     if (bad) return fail(NBG_ERR_NOMEM, "event queue allocation failed");
     Q = EventQueue{p->qn.as<int32_t>(), (int32_t)cap, p->qsys.as<int32_t>(), p->qstep.as<int32_t>(), p->qbody.as<int32_t>(), p->qk.as<int32_t>(),
                    p->qdt0.as<double>(), p->qt.as<double>(), p->qsnap.as<double>(), p->qhdr.as<double>(), p->qstream.as<double>()};
     O = TransitOut{p->btt.as<double>(), p->bdtdq0.as<double>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->RT, p->C};
     evlist = p->bevlist.as<int32_t>();
+    evmask = p->bevmask.as<uint32_t>();
   }
   if (grad && detect) {
     const size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
@@ -642,10 +676,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     double* tkerr = kahan_time ? p->bterr.as<double>() : nullptr;
     if (grad)
       traj_kernel<true, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), detect, ti, t0, done, h_intr,
-                                                          p->bntt.as<int32_t>(), Q, evlist, kahan_time, tkerr);
+                                                          p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr);
     else
       traj_kernel<false, false><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
-                                                            Q, evlist, kahan_time, tkerr);
+                                                            Q, evlist, evmask, kahan_time, tkerr);
     tm.end();
     p->launches++;
     if (detect) {
@@ -656,24 +690,43 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       tm.end();
       p->launches++;
     }
+    if (grad && use_rx) {
+      tm.begin(5);
+      if (launch_phi_dense(p->stream, n, p->bstream.as<double>(), ld, nsys, nullptr, s)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      p->launches++;
+      if (detect) {
+        if (launch_phi_dense(p->stream, n, Q.stream, (size_t)Q.cap, Q.cap, Q.n, 1)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+        p->launches++;
+      }
+      tm.end();
+    }
     if (grad) {
       tm.begin(2);
       if (use_rx) {
         const int32_t* evl = detect ? evlist : nullptr;
+        const uint32_t* evm = detect ? evmask : nullptr;
         double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>(), *Jb = p->bJbak.as<double>();
         const double* strm = p->bstream.as<double>();
         int rc = 0;
         switch (n) {
-          case 2: rc = launch_jac_rx<2, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 3: rc = launch_jac_rx<3, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 4: rc = launch_jac_rx<4, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 5: rc = launch_jac_rx<5, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 6: rc = launch_jac_rx<6, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
-          case 7: rc = launch_jac_rx<7, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O); break;
+          case 2: rc = launch_jac_rx<2, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 3: rc = launch_jac_rx<3, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 4: rc = launch_jac_rx<4, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 5: rc = launch_jac_rx<5, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 6: rc = launch_jac_rx<6, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 7: rc = launch_jac_rx<7, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
           default:
-            if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O);
-            else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O);
-            else rc = launch_jac_rx<8, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, Q, ti, O);
+            // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
+            if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 12) rc = launch_jac_rx<8, 2, false>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 14) rc = launch_jac_rx<8, 4, false>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 22) rc = launch_jac_rx<8, 2, true, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 32) rc = launch_jac_rx<8, 2, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 18) rc = launch_jac_rx<8, 8, false, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 34) rc = launch_jac_rx<8, 4, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 38) rc = launch_jac_rx<8, 8, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else rc = launch_jac_rx<8, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
             break;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
@@ -749,7 +802,7 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
   DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
-                   &p->bstream, &p->bevlist, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
+                   &p->bstream, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
                    &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters};
   for (auto* b : all) b->release();
   for (auto& b : p->stage) b.release();
@@ -854,7 +907,7 @@ static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e
   float tot = 0;
   cudaEventElapsedTime(&tot, e0, e1);
   p->timings[4] = tot;
-  p->timings[3] = tot - p->timings[0] - p->timings[1] - p->timings[2];
+  p->timings[3] = tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5];
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);
@@ -1006,9 +1059,9 @@ int32_t nbg_counters_reset(nbg_plan* p) {
   CK(cudaStreamSynchronize(p->stream));
   return NBG_OK;
 }
-int32_t nbg_last_timings(nbg_plan* p, double* ms5) {
-  if (!p || !ms5) return fail(NBG_ERR_ARG, "NULL argument");
-  for (int q = 0; q < 5; ++q) ms5[q] = p->timings[q];
+int32_t nbg_last_timings(nbg_plan* p, double* ms8) {
+  if (!p || !ms8) return fail(NBG_ERR_ARG, "NULL argument");
+  for (int q = 0; q < 8; ++q) ms8[q] = p->timings[q];
   return NBG_OK;
 }
 int64_t nbg_cuda_stream(nbg_plan* p) { return p ? (int64_t)(intptr_t)p->stream : 0; }

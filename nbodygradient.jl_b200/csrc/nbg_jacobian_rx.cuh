@@ -42,10 +42,12 @@ template <int N> struct RxState {
   double je[N][3];
 };
 
-// async copy of one step's operator block (sf doubles, 4-packed layout) into shared memory
-__device__ __forceinline__ void rx_fetch(double* dst, const double* base, size_t stride, size_t idx, int ngroups, int tid, int nthr) {
-  for (int g = tid; g < ngroups; g += nthr) {
-    const double* src = base + ((size_t)g * stride + idx) * 4;
+// async copy of one step's operator block (4-packed stream layout) into shared memory: the first g0 groups (Kepler
+// records) and g1 groups starting at group `skip` (dense phisalpha operator), packed back to back
+__device__ __forceinline__ void rx_fetch(double* dst, const double* base, size_t stride, size_t idx, int g0, int skip, int g1, int tid, int nthr) {
+  for (int g = tid; g < g0 + g1; g += nthr) {
+    const int gg = g < g0 ? g : g - g0 + skip;
+    const double* src = base + ((size_t)gg * stride + idx) * 4;
     __pipeline_memcpy_async(dst + 4 * g, src, 16);
     __pipeline_memcpy_async(dst + 4 * g + 2, src + 2, 16);
   }
@@ -91,18 +93,24 @@ __device__ __forceinline__ void rx_pair(RxState<N>& S, const double* __restrict_
     w[k] = s + u;
   }
   const double2 mm = *reinterpret_cast<const double2*>(R + KF_MI);
-  double ai[3], aj[3];
+  // comp_sum_matrix! (utils.jl:36-46) with the scaling by the mass fractions folded into its first addition:
+  // err + m w is formed by one FMA (one rounding instead of two)
+  double ei[3], ej[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { ai[k] = mm.y * w[k]; aj[k] = -mm.x * w[k]; }
-  if (c == ci || c == cj) {
+  for (int k = 0; k < 3; ++k) { ei[k] = fma(mm.y, w[k], S.je[PA][k]); ej[k] = fma(-mm.x, w[k], S.je[PB][k]); }
+  if (c == ci || c == cj) {  // mass columns of the two bodies: rank-one terms of jac_ij (ahl21.jl:743-750)
     const double* mb = R + 38 + 12 * half + (c == ci ? 0 : 6);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { ai[k] += mb[k]; aj[k] += mb[3 + k]; }
+    for (int k = 0; k < 3; ++k) { ei[k] += mb[k]; ej[k] += mb[3 + k]; }
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ksum_m(S.jv[PA][k], S.je[PA][k], ai[k]);
-    ksum_m(S.jv[PB][k], S.je[PB][k], aj[k]);
+    const double ti = __dadd_rn(S.jv[PA][k], ei[k]);
+    S.je[PA][k] = __dadd_rn(ei[k], __dsub_rn(S.jv[PA][k], ti));
+    S.jv[PA][k] = ti;
+    const double tj = __dadd_rn(S.jv[PB][k], ej[k]);
+    S.je[PB][k] = __dadd_rn(ej[k], __dsub_rn(S.jv[PB][k], tj));
+    S.jv[PB][k] = tj;
   }
 }
 
@@ -125,141 +133,167 @@ template <int N> __device__ __forceinline__ void rx_fold(RxState<N>& S) {
 // ---- phisalpha as a DENSE operator -----------------------------------------------------------------------------
 // jac_phi (ahl21.jl:635-693) is nonzero only in its v rows x {x, m} columns.  Applying it pair by pair in factored form
 // costs ~85 FP64 instructions per pair and thread (r01 profile: 45% of the kernel's FP64 issue for 5% of the canonical
-// flops); as a dense 3N x 3N block it is 9N^2/2 DFMA per thread.  The trajectory kernel still streams the compact
-// per-pair records (PF doubles); the block assembles the dense blocks cooperatively in shared memory once per step:
+// flops); as a dense 3N x 3N block it is 9N^2/2 DFMA per thread.  The trajectory kernel streams compact per-pair records
+// (PF doubles); phi_dense_kernel (one thread per system, step and body i; lanes = systems) expands them into the dense
+// blocks between the trajectory and the Jacobian kernel:
 //   a_i = - sum_d G m_d r_id / r^3,   T_p = G (I/r^3 - 3 r r^T / r^5),   S_p = fac1 (3 r r^T - r^2 I)      (p = pair)
-//   Ax[i][d] = m_d T_id (d != i),  Ax[i][i] = - sum_l Ax[i][l];   Am[i][d] = - G r_id / r^3 (d != i),  Am[i][i] = 0
+//   Ax[i][d] = m_d T_id (d != i),  Ax[i][i] = - sum_l m_l T_il;   Am[i][d] = - G r_id / r^3 (d != i),  Am[i][i] = 0
 //   Phi_x[i][d] = sum_{j != i} m_j S_ij (Ax[i][d] - Ax[j][d])  +  (d == i ? sum_j m_j Rm_ij : - m_d Rm_id)
 //   Phi_m[i][d] = sum_{j != i} m_j S_ij (Am[i][d] - Am[j][d])  +  (d == i ? sum_j m_j us_ij r_ij : m_d us_id r_id + F_id)
 // with r_ij, F_ij oriented from body i (sign flips for i > j); same linear operator as the reference's jac_phi.
-template <int N> struct RxPhi {
-  static constexpr int NA = (N + 1) / 2;        // bodies whose x rows the x half multiplies; the v half takes the rest
-  static constexpr int KIN = 3 * NA;            // inputs per half (zero padded when N is odd)
-  static constexpr int PHX = 0;                 // [half][3N rows][KIN]
-  static constexpr int PHM = PHX + 2 * 3 * N * KIN;  // [3N rows][N]
-  static constexpr int AX = PHM + 3 * N * N;    // [i][d][6]  symmetric 3x3: xx xy xz yy yz zz
-  static constexpr int AM = AX + 6 * N * N;     // [i][d][3]
-  static constexpr int SIZE = AM + 3 * N * N;   // doubles of scratch
-  static constexpr bool ALIAS = SIZE <= (N * (N - 1) / 2) * KF;  // fits in the (dead) ascending-sweep records of the current buffer
-};
 __device__ __forceinline__ int rx_pair_index(int n, int a, int b) { return a * n - a * (a + 1) / 2 + (b - a - 1); }  // a < b
 
-template <int N> __device__ __forceinline__ void rx_phi_assemble(const double* __restrict__ PH, double* __restrict__ W, int tid, int nthr) {
-  using L = RxPhi<N>;
-  // stage A: off-diagonal blocks of Ax, Am
-  for (int t = tid; t < N * N; t += nthr) {
-    const int i = t / N, d = t % N;
-    if (i != d) {
-      const double* R = PH + rx_pair_index(N, i < d ? i : d, i < d ? d : i) * PF;
-      const double sg = i < d ? 1.0 : -1.0;
-      const double r0 = R[PF_R], r1 = R[PF_R + 1], r2 = R[PF_R + 2], g3 = R[PF_G3], g5 = R[PF_G5];
-      const double md = i < d ? R[PF_MJ] : R[PF_MI];
-      double* a = W + L::AX + 6 * t;
-      a[0] = md * (g3 - g5 * r0 * r0); a[1] = md * (-g5 * r0 * r1); a[2] = md * (-g5 * r0 * r2);
-      a[3] = md * (g3 - g5 * r1 * r1); a[4] = md * (-g5 * r1 * r2); a[5] = md * (g3 - g5 * r2 * r2);
-      double* am = W + L::AM + 3 * t;
-      am[0] = -sg * g3 * r0; am[1] = -sg * g3 * r1; am[2] = -sg * g3 * r2;
-    } else {
-      double* am = W + L::AM + 3 * t;
-      am[0] = 0.0; am[1] = 0.0; am[2] = 0.0;
+// blk: this step's (or this queued transit's) operator block; stride/idx as in Emit/Src; i: body whose v rows are formed
+template <int N> __device__ __forceinline__ void phi_dense_rows(double* __restrict__ blk, size_t stride, size_t idx, int i) {
+  constexpr int P = N * (N - 1) / 2;
+  const double* __restrict__ PH = blk + ((size_t)(2 * P * KF / 4) * stride + idx) * 4;  // group 0 of record 0
+  double* __restrict__ OUT = blk + ((size_t)(P * (2 * KF + PF) / 4) * stride + idx) * 4;
+  const size_t gs = stride * 4;  // doubles between consecutive groups of one system
+  auto grp = [&](int p, int g) { return reinterpret_cast<const double2*>(PH + (size_t)(p * (PF / 4) + g) * gs); };
+  // T (symmetric 3x3 as xx xy xz yy yz zz) and gam = G (x_a - x_b) / r^3 of the pair {a, b}, oriented from a
+  struct TG { double T[6], gam[3], ma, mb; };
+  auto load_tg = [&](int a, int b) {
+    const int p = rx_pair_index(N, a < b ? a : b, a < b ? b : a);
+    const double2 u = __ldg(grp(p, 0)), v = __ldg(grp(p, 0) + 1), e = __ldg(grp(p, 1)), f = __ldg(grp(p, 1) + 1);
+    const double r0 = u.x, r1 = u.y, r2 = v.x, g3 = v.y, g5 = e.x, mi = e.y, mj = f.x;
+    const double sg = a < b ? 1.0 : -1.0;
+    TG o;
+    o.T[0] = g3 - g5 * r0 * r0; o.T[1] = -g5 * r0 * r1; o.T[2] = -g5 * r0 * r2;
+    o.T[3] = g3 - g5 * r1 * r1; o.T[4] = -g5 * r1 * r2; o.T[5] = g3 - g5 * r2 * r2;
+    o.gam[0] = sg * g3 * r0; o.gam[1] = sg * g3 * r1; o.gam[2] = sg * g3 * r2;
+    o.ma = a < b ? mi : mj; o.mb = a < b ? mj : mi;
+    return o;
+  };
+#pragma unroll 1
+  for (int d = 0; d < N; ++d) {
+    // Ax[d][d] = - sum_l m_l T_dl; m_d
+    double diag[6] = {0, 0, 0, 0, 0, 0}, md = 0.0;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      if (l == d) continue;
+      const TG t = load_tg(d, l);
+      md = t.ma;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) diag[q] = fma(-t.mb, t.T[q], diag[q]);
     }
-  }
-  if (N & 1)  // zero padding of the v half's unused inputs
-    for (int t = tid; t < 3 * N * 3; t += nthr) W[L::PHX + (3 * N + t / 3) * L::KIN + (L::KIN - 3) + t % 3] = 0.0;
-  __syncthreads();
-  // stage B: diagonal blocks
-  for (int t = tid; t < 6 * N; t += nthr) {
-    const int i = t / 6, q = t % 6;
-    double s = 0.0;
-    for (int l = 0; l < N; ++l)
-      if (l != i) s -= W[L::AX + 6 * (i * N + l) + q];
-    W[L::AX + 6 * (i * N + i) + q] = s;
-  }
-  __syncthreads();
-  // stage C: one task per (i, d, input column): p < 3 an x column of body d, p == 3 its mass column
-  for (int t = tid; t < N * N * 4; t += nthr) {
-    const int p = t & 3, d = (t >> 2) % N, i = (t >> 2) / N;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    // A[b][d]: x part (6) and mass part (3)
+    auto Aget = [&](int b, double (&ax)[6], double (&am)[3]) {
+      if (b == d) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ax[q] = diag[q];
+        am[0] = 0.0; am[1] = 0.0; am[2] = 0.0;
+      } else {
+        const TG t = load_tg(d, b);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ax[q] = md * t.T[q];
+        am[0] = t.gam[0]; am[1] = t.gam[1]; am[2] = t.gam[2];
+      }
+    };
+    double axi[6], ami[3];
+    Aget(i, axi, ami);
+    double acc[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[k][q] = 0.0;
+#pragma unroll
     for (int j = 0; j < N; ++j) {
       if (j == i) continue;
-      const double* R = PH + rx_pair_index(N, i < j ? i : j, i < j ? j : i) * PF;
+      const int p = rx_pair_index(N, i < j ? i : j, i < j ? j : i);
+      const double2 a = __ldg(grp(p, 0)), b = __ldg(grp(p, 0) + 1), e = __ldg(grp(p, 1)), f = __ldg(grp(p, 1) + 1), g = __ldg(grp(p, 2));
+      const double r[3] = {a.x, a.y, b.x};
+      const double mj = i < j ? f.x : e.y, fac1 = f.y, rsq = g.x, us = g.y;
       const double sg = i < j ? 1.0 : -1.0;
-      const double mj = i < j ? R[PF_MJ] : R[PF_MI];
-      const double r0 = R[PF_R], r1 = R[PF_R + 1], r2 = R[PF_R + 2], fac1 = R[PF_FAC1], rsq = R[PF_R2];
-      double u0, u1, u2;  // column p of A[i][d] - A[j][d]
-      if (p < 3) {
-        const double* ai = W + L::AX + 6 * (i * N + d);
-        const double* aj = W + L::AX + 6 * (j * N + d);
-        // symmetric storage: column p of [0 1 2; 1 3 4; 2 4 5]
-        const int q0 = p, q1 = p == 0 ? 1 : (p == 1 ? 3 : 4), q2 = p == 0 ? 2 : (p == 1 ? 4 : 5);
-        u0 = ai[q0] - aj[q0]; u1 = ai[q1] - aj[q1]; u2 = ai[q2] - aj[q2];
-      } else {
-        const double* ai = W + L::AM + 3 * (i * N + d);
-        const double* aj = W + L::AM + 3 * (j * N + d);
-        u0 = ai[0] - aj[0]; u1 = ai[1] - aj[1]; u2 = ai[2] - aj[2];
+      double axj[6], amj[3];
+      Aget(j, axj, amj);
+      double u[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) u[q] = axi[q] - axj[q];
+      // symmetric storage [0 1 2; 1 3 4; 2 4 5]: column q of the difference; column 3 = mass part
+      const double col[4][3] = {{u[0], u[1], u[2]}, {u[1], u[3], u[4]}, {u[2], u[4], u[5]}, {ami[0] - amj[0], ami[1] - amj[1], ami[2] - amj[2]}};
+      double ev[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double ru = 3.0 * (r[0] * col[q][0] + r[1] * col[q][1] + r[2] * col[q][2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ev[q][k] = fac1 * (r[k] * ru - rsq * col[q][k]);
       }
-      const double ru = 3.0 * (r0 * u0 + r1 * u1 + r2 * u2);
-      double e0 = fac1 * (r0 * ru - rsq * u0), e1 = fac1 * (r1 * ru - rsq * u1), e2 = fac1 * (r2 * ru - rsq * u2);
-      if (p < 3) {
-        if (d == i) { e0 += R[PF_RM + p]; e1 += R[PF_RM + 3 + p]; e2 += R[PF_RM + 6 + p]; }
-        else if (d == j) { e0 -= R[PF_RM + p]; e1 -= R[PF_RM + 3 + p]; e2 -= R[PF_RM + 6 + p]; }
-        acc0 = fma(mj, e0, acc0); acc1 = fma(mj, e1, acc1); acc2 = fma(mj, e2, acc2);
-      } else {
-        if (d == i || d == j) { const double us = sg * R[PF_US]; e0 = fma(us, r0, e0); e1 = fma(us, r1, e1); e2 = fma(us, r2, e2); }
-        acc0 = fma(mj, e0, acc0); acc1 = fma(mj, e1, acc1); acc2 = fma(mj, e2, acc2);
-        if (d == j) { acc0 = fma(sg, R[PF_F], acc0); acc1 = fma(sg, R[PF_F + 1], acc1); acc2 = fma(sg, R[PF_F + 2], acc2); }
+      if (d == i || d == j) {
+        const double2 g1 = __ldg(grp(p, 2) + 1), h0 = __ldg(grp(p, 3)), h1 = __ldg(grp(p, 3) + 1), k0 = __ldg(grp(p, 4)), k1 = __ldg(grp(p, 4) + 1),
+                      l0 = __ldg(grp(p, 5));
+        const double F[3] = {g1.x, g1.y, h0.x};
+        const double Rm[9] = {h0.y, h1.x, h1.y, k0.x, k0.y, k1.x, k1.y, l0.x, l0.y};
+        const double sr = d == i ? 1.0 : -1.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) ev[q][k] = fma(sr, Rm[3 * k + q], ev[q][k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ev[3][k] = fma(sg * us, r[k], ev[3][k]);
+        if (d == j) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc[k][3] = fma(sg, F[k], acc[k][3]);
+        }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k][q] = fma(mj, ev[q][k], acc[k][q]);
     }
-    if (p < 3) {
-      const int hf = d >= L::NA ? 1 : 0, col = 3 * (d - hf * L::NA) + p;
-      double* o = W + L::PHX + (hf * 3 * N + 3 * i) * L::KIN + col;
-      o[0] = acc0; o[L::KIN] = acc1; o[2 * L::KIN] = acc2;
-    } else {
-      double* o = W + L::PHM + (3 * i) * N + d;
-      o[0] = acc0; o[N] = acc1; o[2 * N] = acc2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double2* o = reinterpret_cast<double2*>(OUT + (size_t)((3 * i + k) * N + d) * gs);
+      o[0] = make_double2(acc[k][0], acc[k][1]);
+      o[1] = make_double2(acc[k][2], acc[k][3]);
     }
   }
-  __syncthreads();
 }
 
-// jac_step (+)= jac_phi * jac_step with the dense blocks of rx_phi_assemble; jv/je at offset OFF (position p holds
-// body (OFF + p) mod N).  Each half multiplies its KIN inputs into all 3N outputs, the v half adds the two partial sums.
+// jac_step (+)= jac_phi * jac_step with the dense operator W (layout of phi_dense_fields) staged in shared memory;
+// jv/je at offset OFF (position p holds body (OFF + p) mod N).  The x half multiplies the x rows of bodies 0..NA-1, the
+// v half (which receives them by shuffle) those of bodies NA..N-1, each into all 3N outputs; the v half adds the two.
 template <int N, int OFF> __device__ __forceinline__ void rx_phisalpha_dense(RxState<N>& S, const double* __restrict__ W, int half, int c) {
-  using L = RxPhi<N>;
-  double in[L::KIN];
-  static_for<0, L::NA>([&](auto Qc) {
+  constexpr int NA = (N + 1) / 2;
+  double in[NA][3];
+  static_for<0, NA>([&](auto Qc) {
     constexpr int q = decltype(Qc)::value;
     constexpr int pa = (q - OFF + 2 * N) % N;              // position of body q (x half's input)
-    constexpr int bb = L::NA + q;                          // body whose x rows the v half receives
+    constexpr int bb = NA + q;                             // body whose x rows the v half receives
     if constexpr (bb < N) {
       constexpr int pb = (bb - OFF + 2 * N) % N;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const double got = shx(S.jv[pb][k]);
-        in[3 * q + k] = half ? got : S.jv[pa][k];
+        in[q][k] = half ? got : S.jv[pa][k];
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) in[3 * q + k] = half ? 0.0 : S.jv[pa][k];
+      for (int k = 0; k < 3; ++k) in[q][k] = half ? 0.0 : S.jv[pa][k];
     }
   });
-  // mass column of body dm (or -1): the v half adds Phi_m[:, dm]
-  const int dm = (c % 7 == 6 && c < 7 * N) ? c / 7 : -1;
-  const double* __restrict__ Wh = W + L::PHX + half * 3 * N * L::KIN;
+  const int dm = (c % 7 == 6 && c < 7 * N) ? c / 7 : -1;   // this column is the mass column of body dm
+  const int d0 = half ? (NA < N ? NA : 0) : 0;             // first body of this half's inputs (odd N: last v-half slot is padding)
   static_for<0, N>([&](auto Bc) {
     constexpr int b = decltype(Bc)::value;
     constexpr int pos = (b - OFF + 2 * N) % N;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double* __restrict__ row = Wh + (3 * b + k) * L::KIN;
+      const double* __restrict__ row = W + ((3 * b + k) * N + d0) * 4;
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int t = 0; t + 1 < L::KIN; t += 2) { s0 = fma(row[t], in[t], s0); s1 = fma(row[t + 1], in[t + 1], s1); }
-      if (L::KIN & 1) s0 = fma(row[L::KIN - 1], in[L::KIN - 1], s0);
-      double part = s0 + s1;
+      for (int q = 0; q < NA; ++q) {
+        // odd N: the v half's last input slot is zero padding; point it at a valid weight instead of reading past the row
+        const int qq = ((N & 1) && q == NA - 1 && half) ? q - 1 : q;
+        const double2 w01 = *reinterpret_cast<const double2*>(row + 4 * qq);
+        const double w2 = row[4 * qq + 2];
+        s0 = fma(w01.x, in[q][0], s0);
+        s1 = fma(w01.y, in[q][1], s1);
+        s0 = fma(w2, in[q][2], s0);
+      }
+      const double part = s0 + s1;
       const double other = shx(part);
       double dv = part + other;
-      if (dm >= 0) dv += W[L::PHM + (3 * b + k) * N + dm];
+      if (dm >= 0) dv += W[((3 * b + k) * N + dm) * 4 + 3];
       // comp_sum_matrix!(jac_step, jac_error, jac_phi * jac_step): v rows get dv, x rows a zero addend (fold)
       ksum_m(S.jv[pos][k], S.je[pos][k], half == 1 ? dv : 0.0);
     }
@@ -318,21 +352,20 @@ template <int N, int U, bool SYNC = true> struct RxSweep {
   }
 };
 
-// one AHL21 Jacobian step from a staged operator block; offset 0 (identity) on entry and exit.
-// scr: scratch for the dense phisalpha blocks (the block's own ascending records when RxPhi<N>::ALIAS).
-template <int N, int U>
-__device__ __forceinline__ void rx_step(RxState<N>& S, double* __restrict__ blk, double* __restrict__ scr, double h2, int half, int c, int tid, int nthr) {
+// one AHL21 Jacobian step from a staged operator block [2P Kepler records | dense phisalpha operator];
+// offset 0 (identity) on entry and exit.
+template <int N, int U, bool SYNC = true>
+__device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c) {
   constexpr int P = N * (N - 1) / 2;
-  using SW = RxSweep<N, U>;
+  using SW = RxSweep<N, U, SYNC>;
   auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(S.je); };
   auto pair = [&](auto PA, auto PB, const double* R, int bi, int bj) {
     rx_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, half, c, 7 * bi + 6, 7 * bj + 6);
   };
   rx_drift<N>(S, h2, half);
   rx_fold<N>(S);
-  SW::asc(rotate, blk, KF, pair);                                          // offset 0 -> A1; ends with a block barrier
-  rx_phi_assemble<N>(blk + 2 * P * KF, scr, tid, nthr);
-  rx_phisalpha_dense<N, SW::A1>(S, scr, half, c);                          // A1 -> A1
+  SW::asc(rotate, blk, KF, pair);                                          // offset 0 -> A1
+  rx_phisalpha_dense<N, SW::A1>(S, blk + 2 * P * KF, half, c);             // A1 -> A1
   rotate(std::integral_constant<int, SW::KTOP * U - SW::A1>{});            // A1 -> KTOP*U
   SW::desc(rotate, blk + P * KF, KF, pair);                                // -> 0
   rx_drift<N>(S, h2, half);

@@ -36,21 +36,25 @@ __host__ __device__ constexpr int kf_ci7(int r) { return r < 3 ? 38 + r : 50 + (
 __host__ __device__ constexpr int kf_cj7(int r) { return r < 3 ? 41 + r : 53 + (r - 3); }    // rows j, col m_i
 __host__ __device__ constexpr int kf_ci14(int r) { return r < 3 ? 44 + r : 56 + (r - 3); }   // rows i, col m_j
 __host__ __device__ constexpr int kf_cj14(int r) { return r < 3 ? 47 + r : 59 + (r - 3); }   // rows j, col m_j
-// phisalpha record fields
+// phisalpha record fields, grouped by 4 (one 32-byte sector each) in the order the dense-operator kernel needs them
 constexpr int PF_R = 0;      // 3: r_ij
 constexpr int PF_G3 = 3;     // G / r^3
-constexpr int PF_FAC1 = 4;   // coeff / r^5
-constexpr int PF_R2 = 5;     // r^2
-constexpr int PF_US = 6;     // 2 G fac1 / r   (mass-sum derivative is US * r_ij)
-constexpr int PF_RM = 7;     // 9: dF/dr [k][p]  (index 3*k + p)
-constexpr int PF_F = 16;     // 3: F_ij
-constexpr int PF_MI = 19;    // m_i
-constexpr int PF_MJ = 20;    // m_j
-constexpr int PF_G5 = 21;    // 3 G / r^5
+constexpr int PF_G5 = 4;     // 3 G / r^5
+constexpr int PF_MI = 5;     // m_i
+constexpr int PF_MJ = 6;     // m_j
+constexpr int PF_FAC1 = 7;   // coeff / r^5
+constexpr int PF_R2 = 8;     // r^2
+constexpr int PF_US = 9;     // 2 G fac1 / r   (mass-sum derivative is US * r_ij)
+constexpr int PF_F = 10;     // 3: F_ij
+constexpr int PF_RM = 13;    // 9: dF/dr [k][p]  (index 3*k + p)
 
 __host__ __device__ inline int npairs(int n) { return n * (n - 1) / 2; }
-// doubles per system per step in the operator stream
-__host__ __device__ inline size_t step_fields(int n) { return (size_t)npairs(n) * (2 * KF + PF); }
+// doubles per system per step in the operator stream: [2P Kepler records | P phisalpha records | dense phisalpha operator]
+// dense operator (written by phi_dense_kernel, read by the register-resident Jacobian kernel): element
+// ((3 i + k) N + d) 4 + p = d v_i[k] / d x_d[p] for p < 3, d v_i[k] / d m_d for p = 3.
+__host__ __device__ inline size_t phi_dense_fields(int n) { return (size_t)12 * n * n; }
+__host__ __device__ inline size_t phi_dense_offset(int n) { return (size_t)npairs(n) * (2 * KF + PF); }
+__host__ __device__ inline size_t step_fields(int n) { return phi_dense_offset(n) + phi_dense_fields(n); }
 
 struct Body {
   double x[3 * NMAX], v[3 * NMAX], xe[3 * NMAX], ve[3 * NMAX], m[NMAX];

@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
-LIB = os.path.join(CSRC, "libnbgrad_b200.so")
+LIB = os.environ.get("NBGRAD_B200_LIB") or os.path.join(CSRC, "libnbgrad_b200.so")  # env override: A/B builds on the GPU box
 SOURCES = ["nbg_b200.cu"]
 HEADERS = ["nbg_kepler.cuh", "nbg_step.cuh", "nbg_jacobian.cuh", os.path.join("..", "..", "include", "nbgrad.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]

@@ -182,9 +182,9 @@ class Integrator:
         return _plan(s.n, s.nsys, self.device, self.stream_budget)
 
     def _timings(self, plan):
-        ms = np.zeros(5)
+        ms = np.zeros(8)
         check(_lib.lib().nbg_last_timings(plan, ptr(ms)))
-        self.last_timings = dict(traj_ms=ms[0], transit_ms=ms[1], jac_ms=ms[2], other_ms=ms[3], total_ms=ms[4])
+        self.last_timings = dict(traj_ms=ms[0], transit_ms=ms[1], jac_ms=ms[2], other_ms=ms[3], total_ms=ms[4], phi_dense_ms=ms[5])
 
     def __call__(self, s, arg=None, grad=True):
         if isinstance(arg, _TransitOutput):
