@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsy
   uint32_t st = 0;
   const size_t sf = step_fields(n);
   for (int s = 0; s < nsteps; ++s) {
-    Emit em{EMIT ? stream + (size_t)s * sf * ld : nullptr, ld, (size_t)sys};
+    Emit em{EMIT ? stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys) : nullptr, TILE, (size_t)(sys % TILE)};
     ahl21_step<GRAD, EMIT>(b, dq, n, h, em);
     if (time_mode_kahan) ksum(tnow, terr, h);                      // (intr)(s,N): Integrator.jl:229
     else tnow = t0 + ((double)(istep0 + s + 1) * h);               // Transits.jl:161
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   uint32_t st = (iter >= 20) ? NBG_ST_TRANSIT_ITMAX : 0u;
   if (GRAD) {
     b = b0;
-    Emit em{Q.stream, (size_t)Q.cap, (size_t)e};
+    Emit em{Q.stream + tile_offset(step_fields(n), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
     ahl21_step<true, true>(b, dq, n, dt0, em);
   }
   const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
@@ -231,7 +231,7 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   __syncthreads();
   const size_t sf = step_fields(n);
   for (int s = 0; s < nsteps; ++s) {
-    Src src{stream + (size_t)s * sf * ld, ld, (size_t)sys};
+    Src src{stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys), TILE, (size_t)(sys % TILE)};
     jac_apply_step(S, src, n, M, c, 0.5 * h, tid, nthr);
     if (evlist) {
       for (int i = 0; i < n; ++i) {
@@ -243,7 +243,7 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
         __syncthreads();
         const size_t cap = Q.cap;
         const double dt0 = Q.hdr[7 * cap + slot];
-        Src ev{Q.stream, cap, (size_t)slot};
+        Src ev{Q.stream + tile_offset(sf, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE)};
         jac_apply_step(S, ev, n, M, c, 0.5 * dt0, tid, nthr);
         if (c < M) {
           const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     }
   double* const buf0 = smrx;
   double* const buf1 = smrx + SB;
-  rx_fetch(buf0, stream, ld, (size_t)sys, G0, GSKIP, G1, tid, NT);
+  const size_t ntiles = ld / TILE;
+  rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
   // One loop over work items -- a main step, or the extra step of a queued transit -- so that rx_step<N> (13k
   // instructions, fully unrolled) exists once in the instruction stream.
   double* const bk = Jbak + (size_t)sys * 6 * N * NT + tid;
@@ -314,11 +315,12 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
       __pipeline_wait_prior(0);
       __syncthreads();  // step s operators visible; everyone is done with the other buffer
-      if (s + 1 < nsteps) rx_fetch((s & 1) ? buf0 : buf1, stream + (size_t)(s + 1) * SFS * ld, ld, (size_t)sys, G0, GSKIP, G1, tid, NT);
+      if (s + 1 < nsteps)
+        rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
       h2 = 0.5 * h;
     } else {
       __syncthreads();  // everyone is done with cur
-      rx_fetch(cur, Q.stream, cap, (size_t)slot, G0, GSKIP, G1, tid, NT);
+      rx_fetch(cur, Q.stream + tile_offset(SFS, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE), G0, GSKIP, G1, tid, NT);
       // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
 #pragma unroll
       for (int b = 0; b < N; ++b)
@@ -385,25 +387,25 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
 // Dense phisalpha operator (see nbg_jacobian_rx.cuh): one thread per (system or queued transit, step, body i); the 32
 // lanes of a warp are consecutive systems, so every record read and every output write is a coalesced run of sectors.
 template <int N>
-__global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(double* __restrict__ base, size_t stride, long nitems, const int32_t* __restrict__ nitems_dev,
-                                                           size_t step_elems) {
+__global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(double* __restrict__ base, size_t ntiles, long nitems,
+                                                                         const int32_t* __restrict__ nitems_dev) {
   const long idx = (long)blockIdx.x * 32 + threadIdx.x;
   const long nv = nitems_dev ? min((long)*nitems_dev, nitems) : nitems;
   if (idx >= nv) return;
-  phi_dense_rows<N>(base + (size_t)blockIdx.y * step_elems, stride, (size_t)idx, (int)threadIdx.y);
+  phi_dense_rows<N>(base + tile_offset(step_fields(N), ntiles, blockIdx.y, (size_t)idx), TILE, (size_t)threadIdx.x, (int)threadIdx.y);
 }
-int launch_phi_dense(cudaStream_t st, int n, double* base, size_t stride, long nitems, const int32_t* nitems_dev, int nsteps) {
+// main steps: ntiles = ld / 32, nsteps steps; queued transits: ntiles = 0 (one "step"), nitems_dev = device count of queued transits
+int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long nitems, const int32_t* nitems_dev, int nsteps) {
   if (nitems <= 0 || nsteps <= 0) return 0;
   const dim3 grid((unsigned)((nitems + 31) / 32), (unsigned)nsteps), block(32, n);
-  const size_t se = step_fields(n) * stride;
   switch (n) {
-    case 2: phi_dense_kernel<2><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
-    case 3: phi_dense_kernel<3><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
-    case 4: phi_dense_kernel<4><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
-    case 5: phi_dense_kernel<5><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
-    case 6: phi_dense_kernel<6><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
-    case 7: phi_dense_kernel<7><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
-    case 8: phi_dense_kernel<8><<<grid, block, 0, st>>>(base, stride, nitems, nitems_dev, se); break;
+    case 2: phi_dense_kernel<2><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 3: phi_dense_kernel<3><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 4: phi_dense_kernel<4><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 5: phi_dense_kernel<5><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 6: phi_dense_kernel<6><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 7: phi_dense_kernel<7><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 8: phi_dense_kernel<8><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
     default: return -1;
   }
   return 0;
@@ -547,7 +549,7 @@ struct nbg_plan {
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
   DevBuf stage[8];  // staging for host<->device conversions
   bool has_state = false, jac_valid = false, force_generic_jac = false;
-  int rx_unroll = 2;
+  int rx_unroll = 38;
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
@@ -692,10 +694,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     }
     if (grad && use_rx) {
       tm.begin(5);
-      if (launch_phi_dense(p->stream, n, p->bstream.as<double>(), ld, nsys, nullptr, s)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      if (launch_phi_dense(p->stream, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
       p->launches++;
       if (detect) {
-        if (launch_phi_dense(p->stream, n, Q.stream, (size_t)Q.cap, Q.cap, Q.n, 1)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+        if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
         p->launches++;
       }
       tm.end();

@@ -60,6 +60,16 @@ struct Body {
   double x[3 * NMAX], v[3 * NMAX], xe[3 * NMAX], ve[3 * NMAX], m[NMAX];
 };
 
+// Operator-stream addressing.  Systems (or queued transits) are tiled by 32 -- one warp of the trajectory kernel -- and
+// the block of one step of one tile is contiguous: [step][tile][group of 4 fields][32 systems][4 doubles].  A warp writes
+// 1 KB runs; the Jacobian kernel reads its system's 32-byte sectors 1 KB apart inside one 32*sf*8-byte region (the
+// earlier [group][all systems] layout put every sector of a system's step in a different 2 MB page: the Jacobian kernel
+// ran 1.36x slower on 65,536 systems than on 16,384).
+constexpr int TILE = 32;
+__host__ __device__ inline size_t tile_offset(size_t sf, size_t ntiles, size_t step, size_t item) {
+  return (step * ntiles + item / TILE) * sf * TILE;  // in doubles, from the start of the stream
+}
+
 // Operator-stream writer for this thread's system/slot (idx) out of `stride` systems/slots.
 struct Emit {
   double* base;
