@@ -299,7 +299,7 @@ def main():
         "rates": {"main_steps_per_s": value, "step_equivalents_per_s": world * step_equiv / (ms_max * 1e-3),
                   "jacobian_steps_per_s": world * jac_steps / (ms_max * 1e-3), "transits": int(cnt[3]),
                   "newton_iters_per_transit": float(cnt[1]) / max(1, int(cnt[3]))},
-        "kernel_ms": {names[k]: float(ksum[k]) for k in range(3)} | {"phi_dense_kernel": float(ksum[5]), "other": float(ksum[3]), "total": float(ksum[4])},
+        "kernel_ms": {names[k]: float(ksum[k]) for k in range(3)} | {"phi_dense_kernel": float(ksum[5]), "pair_op_kernel": float(ksum[6]), "other": float(ksum[3]), "total": float(ksum[4])},
         "roofline": {"bound": "fp64", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "traffic": None, "flops": "canonical (SURVEY 8d): F_jac(8)=%d per Jacobian step, F_scalar(8)=%d per trajectory step" %
                      (f_jac(NBODY), f_grad(NBODY) - f_jac(NBODY)),

@@ -61,8 +61,8 @@ struct TransitOut {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-template <bool GRAD, bool EMIT>
-__global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, int detect, int ti,
+template <bool GRAD, int EMIT>
+__global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, double* scal, int detect, int ti,
                                                    double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
                                                    int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err) {
   const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsy
   uint32_t st = 0;
   const size_t sf = step_fields(n);
   for (int s = 0; s < nsteps; ++s) {
-    Emit em{EMIT ? stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys) : nullptr, TILE, (size_t)(sys % TILE)};
+    Emit em{EMIT ? stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys) : nullptr, TILE, (size_t)(sys % TILE),
+            EMIT == 2 ? scal + tile_offset((size_t)2 * npairs(n) * SCF, ld / TILE, (size_t)s, (size_t)sys) : nullptr};
     ahl21_step<GRAD, EMIT>(b, dq, n, h, em);
     if (time_mode_kahan) ksum(tnow, terr, h);                      // (intr)(s,N): Integrator.jl:229
     else tnow = t0 + ((double)(istep0 + s + 1) * h);               // Transits.jl:161
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
     tt2 = tt1;
     tt1 = dt0;
     b = b0;
-    ahl21_step<true, false>(b, dq, n, dt0, none);
+    ahl21_step<true, 0>(b, dq, n, dt0, none);
     const double gs = gsky(b, ti, j);
     const double gd = gdot(b, dq, ti, j);
     const double dt = -gs / gd;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   if (GRAD) {
     b = b0;
     Emit em{Q.stream + tile_offset(step_fields(n), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
-    ahl21_step<true, true>(b, dq, n, dt0, em);
+    ahl21_step<true, 1>(b, dq, n, dt0, em);
   }
   const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
   const double dvx = b.v[3 * j] - b.v[3 * ti], dvy = b.v[3 * j + 1] - b.v[3 * ti + 1];
@@ -384,6 +385,42 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
   }
 }
 
+// Split path, second stage: the Kepler operator records of the main steps.  One thread per (system, step, pair section);
+// the 32 lanes of a warp are the systems of one tile, so the section index (hence drift_first) is uniform in a warp and
+// every load/store is a 1 KB run.  Reads the SCF scalars the trajectory kernel left, runs compute_jacobian_gamma!
+// (ahl21.jl:896-1139) in registers and writes the KF-double record the Jacobian kernel consumes.
+__global__ void __launch_bounds__(128, 2) pair_op_kernel(const double* __restrict__ scal, double* __restrict__ stream, int n, size_t ntiles, long nsys) {
+  const int P = npairs(n);
+  const int sec = blockIdx.z * blockDim.y + threadIdx.y;
+  const long sys = (long)blockIdx.x * TILE + threadIdx.x;
+  if (sec >= 2 * P || sys >= nsys) return;
+  const double* __restrict__ src = scal + tile_offset((size_t)2 * P * SCF, ntiles, blockIdx.y, (size_t)sys) + ((size_t)sec * (SCF / 4) * TILE + threadIdx.x) * 4;
+  double in[SCF];
+#pragma unroll
+  for (int g = 0; g < SCF / 4; ++g) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(src + (size_t)g * TILE * 4));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(src + (size_t)g * TILE * 4) + 1);
+    in[4 * g] = a.x; in[4 * g + 1] = a.y; in[4 * g + 2] = b.x; in[4 * g + 3] = b.y;
+  }
+  double x0[3], v0[3], bim, bjm;
+  KepScal S;
+  scal_unpack(in, x0, v0, S, bim, bjm);
+  double rec[KF];
+  if (S.k == 0.0) {
+#pragma unroll
+    for (int f = 0; f < KF; ++f) rec[f] = 0.0;
+  } else {
+    KepJac J;
+    kepler_jacobian_inl(&S, x0, v0, sec < P, &J);
+    double dl[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { dl[j] = S.fm1 * x0[j] + S.gmh * v0[j]; dl[3 + j] = S.dfdt * x0[j] + S.dgdtm1 * v0[j]; }
+    kepler_record(rec, J, dl, bim, bjm);
+  }
+  Emit em{stream + tile_offset(step_fields(n), ntiles, blockIdx.y, (size_t)sys), TILE, (size_t)threadIdx.x};
+  em.put_record<KF>((size_t)sec * KF, rec);
+}
+
 // Dense phisalpha operator (see nbg_jacobian_rx.cuh): one thread per (system or queued transit, step, body i); the 32
 // lanes of a warp are consecutive systems, so every record read and every output write is a coalesced run of sectors.
 template <int N>
@@ -544,11 +581,11 @@ struct nbg_plan {
   cudaStream_t stream = nullptr;
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
-  DevBuf bJv, bJe, bJbak, bstream, bevlist, bevmask;
+  DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
   DevBuf stage[8];  // staging for host<->device conversions
-  bool has_state = false, jac_valid = false, force_generic_jac = false;
+  bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true;
   int rx_unroll = 38;
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
@@ -622,11 +659,13 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   const size_t jsz = (size_t)6 * n * 7 * n;
   // chunk length from the stream budget
   size_t per_step = sf * ld * 8;
+  const size_t per_step_scal = p->split_traj ? (size_t)2 * npairs(n) * SCF * ld * 8 : 0;
   long S = 1;
   if (grad) {
-    S = (long)std::max<int64_t>(1, std::min<int64_t>(p->stream_budget / (int64_t)per_step, 64));
+    S = (long)std::max<int64_t>(1, std::min<int64_t>(p->stream_budget / (int64_t)(per_step + per_step_scal), 64));
     S = std::min(S, nsteps);
     if (p->bstream.ensure((size_t)S * per_step)) return fail(NBG_ERR_NOMEM, "operator stream allocation failed");
+    if (per_step_scal && p->bscal.ensure((size_t)S * per_step_scal)) return fail(NBG_ERR_NOMEM, "scalar stream allocation failed");
   } else {
     S = std::min<long>(nsteps, 256);
   }
@@ -676,12 +715,32 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     if (detect) CK(cudaMemsetAsync(p->qn.p, 0, 4, p->stream));
     tm.begin(0);
     double* tkerr = kahan_time ? p->bterr.as<double>() : nullptr;
-    if (grad)
-      traj_kernel<true, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), detect, ti, t0, done, h_intr,
-                                                          p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr);
-    else
-      traj_kernel<false, false><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
-                                                            Q, evlist, evmask, kahan_time, tkerr);
+    int s_split = 0;  // steps of this chunk whose Kepler records come from pair_op_kernel (split path)
+    if (grad && p->split_traj) {
+      // dq/dh restarts from zero every step (ahl21.jl:9), so only the last step of the integration needs it: that step
+      // also evaluates the pair Jacobians in the trajectory thread (GRAD = true).  Every step's operator records come from
+      // pair_op_kernel, so jac_step does not depend on how the integration is cut into chunks or calls.
+      const bool last_chunk = done + s == nsteps;
+      const int s_light = last_chunk ? s - 1 : s;
+      s_split = s;
+      if (s_light > 0)
+        traj_kernel<false, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s_light, p->bstream.as<double>(), p->bscal.as<double>(), detect, ti, t0,
+                                                          done, h_intr, p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr);
+      if (s_light < s) {
+        const size_t o = (size_t)s_light;
+        traj_kernel<true, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s - s_light, p->bstream.as<double>() + o * sf * ld,
+                                                         p->bscal.as<double>() + o * 2 * npairs(n) * SCF * ld, detect, ti, t0, done + s_light, h_intr,
+                                                         p->bntt.as<int32_t>(), Q, evlist ? evlist + o * n * ld : nullptr,
+                                                         evmask ? evmask + o * ld : nullptr, kahan_time, tkerr);
+        if (s_light > 0) p->launches++;
+      }
+    } else if (grad) {
+      traj_kernel<true, 1><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
+                                                       p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr);
+    } else {
+      traj_kernel<false, 0><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
+                                                         Q, evlist, evmask, kahan_time, tkerr);
+    }
     tm.end();
     p->launches++;
     if (detect) {
@@ -689,6 +748,14 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
       if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount);
       else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount);
+      tm.end();
+      p->launches++;
+    }
+    if (s_split > 0) {
+      tm.begin(6);
+      const int py = 4;
+      const dim3 grid((unsigned)(ld / TILE), (unsigned)s_split, (unsigned)((2 * npairs(n) + py - 1) / py)), block(TILE, py);
+      pair_op_kernel<<<grid, block, 0, p->stream>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys);
       tm.end();
       p->launches++;
     }
@@ -793,6 +860,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   p->stream_budget = stream_budget_bytes;
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
+  if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
   if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   *out = p;
@@ -804,7 +872,7 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
   DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
-                   &p->bstream, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
+                   &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
                    &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters};
   for (auto* b : all) b->release();
   for (auto& b : p->stage) b.release();
@@ -909,7 +977,7 @@ static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e
   float tot = 0;
   cudaEventElapsedTime(&tot, e0, e1);
   p->timings[4] = tot;
-  p->timings[3] = tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5];
+  p->timings[3] = tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6];
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);

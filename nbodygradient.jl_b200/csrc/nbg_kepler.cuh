@@ -193,8 +193,10 @@ __device__ __noinline__ void kepler_solve(const double* __restrict__ x0, const d
 }
 
 // compute_jacobian_gamma! (ahl21.jl:896-1139, debug = false)
-__device__ __noinline__ void kepler_jacobian(const KepScal* __restrict__ P, const double* __restrict__ x0, const double* __restrict__ v0,
-                                             bool drift_first, KepJac* __restrict__ J) {
+// _inl: inlined into pair_op_kernel (everything in registers); the __noinline__ wrapper below is what the one-thread-per-
+// system kernels call twice per pair (keeps their instruction footprint small).
+__device__ __forceinline__ void kepler_jacobian_inl(const KepScal* __restrict__ P, const double* __restrict__ x0, const double* __restrict__ v0,
+                                                    bool drift_first, KepJac* __restrict__ J) {
   const double gamma = P->gamma, g0 = P->g0, g1 = P->g1, g2 = P->g2, g3 = P->g3, h1 = P->h1, h2 = P->h2, dfdt = P->dfdt, fm1 = P->fm1,
                gmh = P->gmh, dgdtm1 = P->dgdtm1, r0 = P->r0, r = P->r, r0inv = P->r0inv, rinv = P->rinv, k = P->k, h = P->h, beta = P->beta,
                betainv = P->betainv, eta = P->eta, sqb = P->sqb, zeta = P->zeta;
@@ -355,6 +357,10 @@ __device__ __noinline__ void kepler_jacobian(const KepScal* __restrict__ P, cons
     J->jm[j] = mass_x_scale * (dfm1dk2 * x0[j] + mass_x_sign * dgmhdk2 * v0[j]);
     J->jm[3 + j] = mass_v_scale * (ddfdtdk2 * x0[j] + dgdk2 * v0[j]);
   }
+}
+__device__ __noinline__ void kepler_jacobian(const KepScal* __restrict__ P, const double* __restrict__ x0, const double* __restrict__ v0,
+                                             bool drift_first, KepJac* __restrict__ J) {
+  kepler_jacobian_inl(P, x0, v0, drift_first, J);
 }
 
 }  // namespace nbg

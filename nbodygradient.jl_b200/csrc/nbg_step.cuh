@@ -23,6 +23,7 @@ namespace nbg {
 constexpr int NMAX = 16;  // max bodies per system
 constexpr int KF = 64;    // doubles per Kepler-pair operator record
 constexpr int PF = 24;    // doubles per phisalpha-pair operator record
+constexpr int SCF = 32;   // doubles per pair section in the scalar stream of the split path: x0, v0, the 22 scalars of KepScal, m_i, m_j
 
 // Kepler record fields.  The 6x6 block jac_kepler is stored as four 3x3 blocks ordered for the Jacobian kernel's
 // x-rows / v-rows thread halves: [Kxx, Kxv | Kvv, Kvx], then the mass-column terms split the same way.
@@ -75,13 +76,14 @@ struct Emit {
   double* base;
   size_t stride;
   size_t idx;
+  double* sbase = nullptr;  // scalar records of the split path (EMIT == 2): SCF doubles per pair section, same tiling
   // fields are packed in groups of 4 per system (32-byte sectors): element f at ((f/4)*stride + idx)*4 + f%4
   __device__ __forceinline__ void put(size_t f, double val) const { base[((f >> 2) * stride + idx) * 4 + (f & 3)] = val; }
   // a whole record of NF (multiple of 4) doubles starting at field f0 (multiple of 4), as 16-byte stores
-  template <int NF> __device__ __forceinline__ void put_record(size_t f0, const double (&rec)[NF]) const {
+  template <int NF> __device__ __forceinline__ void put_record(size_t f0, const double (&rec)[NF], bool scalars = false) const {
 #pragma unroll
     for (int g = 0; g < NF / 4; ++g) {
-      double2* dst = reinterpret_cast<double2*>(base + (((f0 >> 2) + g) * stride + idx) * 4);
+      double2* dst = reinterpret_cast<double2*>((scalars ? sbase : base) + (((f0 >> 2) + g) * stride + idx) * 4);
       dst[0] = make_double2(rec[4 * g], rec[4 * g + 1]);
       dst[1] = make_double2(rec[4 * g + 2], rec[4 * g + 3]);
     }
@@ -113,7 +115,45 @@ template <bool GRAD> __device__ __forceinline__ void store_body(Body& b, double*
   }
 }
 
-template <bool GRAD, bool EMIT>
+// Packs / unpacks the inputs of kepler_jacobian for the split path (trajectory kernel -> pair_op_kernel).
+__device__ __forceinline__ void scal_pack(double (&rec)[SCF], const double* x0, const double* v0, const KepScal& P, double mi, double mj) {
+  rec[0] = x0[0]; rec[1] = x0[1]; rec[2] = x0[2]; rec[3] = v0[0]; rec[4] = v0[1]; rec[5] = v0[2];
+  rec[6] = P.gamma; rec[7] = P.g0; rec[8] = P.g1; rec[9] = P.g2; rec[10] = P.g3; rec[11] = P.h1; rec[12] = P.h2; rec[13] = P.dfdt;
+  rec[14] = P.fm1; rec[15] = P.gmh; rec[16] = P.dgdtm1; rec[17] = P.r0; rec[18] = P.r; rec[19] = P.r0inv; rec[20] = P.rinv; rec[21] = P.k;
+  rec[22] = P.h; rec[23] = P.beta; rec[24] = P.betainv; rec[25] = P.eta; rec[26] = P.sqb; rec[27] = P.zeta; rec[28] = mi; rec[29] = mj;
+  rec[30] = 0.0; rec[31] = 0.0;
+}
+__device__ __forceinline__ void scal_unpack(const double (&rec)[SCF], double* x0, double* v0, KepScal& P, double& mi, double& mj) {
+  x0[0] = rec[0]; x0[1] = rec[1]; x0[2] = rec[2]; v0[0] = rec[3]; v0[1] = rec[4]; v0[2] = rec[5];
+  P.gamma = rec[6]; P.g0 = rec[7]; P.g1 = rec[8]; P.g2 = rec[9]; P.g3 = rec[10]; P.h1 = rec[11]; P.h2 = rec[12]; P.dfdt = rec[13];
+  P.fm1 = rec[14]; P.gmh = rec[15]; P.dgdtm1 = rec[16]; P.r0 = rec[17]; P.r = rec[18]; P.r0inv = rec[19]; P.rinv = rec[20]; P.k = rec[21];
+  P.h = rec[22]; P.beta = rec[23]; P.betainv = rec[24]; P.eta = rec[25]; P.sqb = rec[26]; P.zeta = rec[27]; mi = rec[28]; mj = rec[29];
+}
+// The Kepler operator record of one pair section from the pair's Jacobian (jac_ij without its identity, ahl21.jl:735-758):
+// the 6x6 block on relative coordinates, the mass fractions, and the four rank-one mass columns.
+__device__ __forceinline__ void kepler_record(double (&rec)[KF], const KepJac& J, const double* dl, double bim, double bjm) {
+  const double mijinv = 1.0 / (bim + bjm);
+  const double mi = bim * mijinv, mj = bjm * mijinv;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) rec[kf_k(r, c)] = J.jk[r][c];
+  rec[KF_MI] = mi;
+  rec[KF_MJ] = mj;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    rec[kf_ci7(r)] = J.jm[r] * bjm;
+    rec[kf_cj7(r)] = -mj * dl[r] * mijinv - kG * mi * J.jk[r][6];
+    rec[kf_ci14(r)] = mi * dl[r] * mijinv + kG * mj * J.jk[r][6];
+    rec[kf_cj14(r)] = -J.jm[r] * bim;
+  }
+  rec[62] = 0.0; rec[63] = 0.0;
+}
+
+// EMIT: 0 = nothing, 1 = full operator records (needs GRAD), 2 = split path: only the inputs of kepler_jacobian are
+// written (SCF doubles per section) and pair_op_kernel builds the records; GRAD = false then (dq/dh restarts from zero at
+// every step, ahl21.jl:9, so only the LAST step of an integration needs it: that one runs with GRAD = true, EMIT = 1).
+template <bool GRAD, int EMIT>
 __device__ __forceinline__ void pair_section(BodyRegs& bi, BodyRegs& bj, double h2, bool drift_first, const Emit& em, size_t rec_base) {
   double x0[3], v0[3], dl[6];
 #pragma unroll
@@ -124,11 +164,17 @@ __device__ __forceinline__ void pair_section(BodyRegs& bi, BodyRegs& bj, double 
   if (gm == 0.0) {
     // Two massless bodies: no interaction.  (The reference returns before touching anything, ahl21.jl:713,
     // and then re-applies the previous pair's stale jac_ij; here the pair is the identity.)
-    if (EMIT) {
+    if (EMIT == 1) {
       double rec[KF];
 #pragma unroll
       for (int f = 0; f < KF; ++f) rec[f] = 0.0;
       em.put_record<KF>(rec_base, rec);
+    }
+    if (EMIT == 2) {
+      double rec[SCF];
+#pragma unroll
+      for (int f = 0; f < SCF; ++f) rec[f] = 0.0;   // k = 0 marks "no interaction"
+      em.put_record<SCF>(rec_base / KF * SCF, rec, true);
     }
     return;
   }
@@ -165,23 +211,15 @@ __device__ __forceinline__ void pair_section(BodyRegs& bi, BodyRegs& bj, double 
       bj.dq[r] = 0.5 * (-mi * J.jk[r][7]) + bj.dq[r] - mi * w[r];
     }
   }
-  if (EMIT) {
+  if (EMIT == 1) {
     double rec[KF];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) rec[kf_k(r, c)] = J.jk[r][c];
-    rec[KF_MI] = mi;
-    rec[KF_MJ] = mj;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      rec[kf_ci7(r)] = J.jm[r] * bj.m;
-      rec[kf_cj7(r)] = -mj * dl[r] * mijinv - kG * mi * J.jk[r][6];
-      rec[kf_ci14(r)] = mi * dl[r] * mijinv + kG * mj * J.jk[r][6];
-      rec[kf_cj14(r)] = -J.jm[r] * bi.m;
-    }
-    rec[62] = 0.0; rec[63] = 0.0;
+    kepler_record(rec, J, dl, bi.m, bj.m);
     em.put_record<KF>(rec_base, rec);
+  }
+  if (EMIT == 2) {
+    double rec[SCF];
+    scal_pack(rec, x0, v0, P, bi.m, bj.m);
+    em.put_record<SCF>(rec_base / KF * SCF, rec, true);
   }
 }
 
@@ -224,7 +262,7 @@ __device__ __noinline__ void phis_force(const double* __restrict__ r, const doub
   out[3] = fac1; out[4] = fac2; out[5] = r2; out[6] = r1;
 }
 
-template <bool GRAD, bool EMIT>
+template <bool GRAD, int EMIT>
 __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, double h, const Emit& em, size_t rec_base) {
   double a[3 * NMAX], da[3 * NMAX];
   const double coeff = 2.0 * (h * h * h) / 96.0 * 2.0 * kG;  // alpha = 2  (ahl21.jl:564)
@@ -318,7 +356,7 @@ __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, do
 
 // dq: d(state)/dh, 6 entries per body (x then v); mass entries are identically zero and not stored.
 // em.base points at this step's region of the operator stream (used when EMIT).
-template <bool GRAD, bool EMIT>
+template <bool GRAD, int EMIT>
 __device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em) {
   const double h2 = 0.5 * h;
   const int P = npairs(n);

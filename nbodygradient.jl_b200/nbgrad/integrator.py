@@ -184,7 +184,7 @@ class Integrator:
     def _timings(self, plan):
         ms = np.zeros(8)
         check(_lib.lib().nbg_last_timings(plan, ptr(ms)))
-        self.last_timings = dict(traj_ms=ms[0], transit_ms=ms[1], jac_ms=ms[2], other_ms=ms[3], total_ms=ms[4], phi_dense_ms=ms[5])
+        self.last_timings = dict(traj_ms=ms[0], transit_ms=ms[1], jac_ms=ms[2], other_ms=ms[3], total_ms=ms[4], phi_dense_ms=ms[5], pair_op_ms=ms[6])
 
     def __call__(self, s, arg=None, grad=True):
         if isinstance(arg, _TransitOutput):
