@@ -61,8 +61,11 @@ struct TransitOut {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// Launch bounds: the light (split-path) instantiation is capped at 128 registers so that 4 blocks fit an SM: a thread owns
+// a system for the whole chunk, so 65,536 systems must all be resident at once (148 SMs x 512 threads) or the kernel pays
+// a nearly empty second wave.
 template <bool GRAD, int EMIT>
-__global__ void __launch_bounds__(128) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, double* scal, int detect, int ti,
+__global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, double* scal, int detect, int ti,
                                                    double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
                                                    int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err) {
   const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
