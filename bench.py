@@ -130,9 +130,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    elb, x, v, jac_init = make_batch(max(cores * 2, 8))
+    nsys = cores * args.ref_systems_per_core
+    elb, x, v, jac_init = make_batch(max(nsys, 8))
     m = np.ascontiguousarray(elb[:, :, 0])
-    nsys = cores * 2
     window = args.ref_window
     for _ in range(args.warmup):
         cpu_run(min(nsys, cores), max(4, window // 8), cores, x, v, m, jac_init)
@@ -160,7 +160,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nsys", type=int, default=65536)
     ap.add_argument("--window", type=int, default=64)
-    ap.add_argument("--ref-window", type=int, default=128)
+    ap.add_argument("--ref-window", type=int, default=4096, help="steps per system of the CPU-baseline sample")
+    ap.add_argument("--ref-systems-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -278,22 +279,33 @@ def main():
     L.nbg_fp64_peak(C.c_int32(local), C.byref(tfl), C.byref(pms))
     peak = tfl.value
     names = ["traj_kernel", "transit_kernel", "jac_kernel"]
-    dom = int(np.argmax(ksum[:3]))
+    dom = 2 if ksum[2] >= max(ksum[0] + ksum[6], ksum[1]) else int(np.argmax(ksum[:2]))
     jac_steps = float(cnt[5])        # Jacobian system-steps applied (main + transit final steps)
     step_equiv = float(cnt[0] + cnt[1] + cnt[2])
     flops = {0: (f_grad(NBODY) - f_jac(NBODY)) * float(cnt[0]), 1: (f_grad(NBODY) - f_jac(NBODY)) * float(cnt[1] + cnt[2]),
              2: f_jac(NBODY) * jac_steps}
-    achieved = flops[dom] / (ksum[dom] * 1e-3) / 1e12
+    dom_ms = ksum[dom] + (ksum[6] if dom == 0 else 0.0)
+    achieved = flops[dom] / (dom_ms * 1e-3) / 1e12
+    # measured DRAM traffic of the dominant kernel (ncu --set full, profiles/r01_traffic.json), scaled to this run's launches
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and dom == 2:
+        tj = json.load(open(tpath))
+        traffic = tj["jac_rx_kernel"]["dram_bytes_per_jacobian_step"] * jac_steps / max(1, int(cnt[7]))
     path_achieved = f_grad(NBODY) * step_equiv / (ksum[4] * 1e-3) / 1e12
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    stream_bytes = (28 * (2 * 64 + 24)) * 8.0 * (float(cnt[0]) + float(cnt[2]))  # operator stream written once, read once
-    hbm_gbs = 2 * stream_bytes / (ksum[4] * 1e-3) / 1e9
+    # algorithmic HBM bytes per main system-step: scalars (written, read), compact phisalpha records (written, read), Kepler records
+    # (written, read), dense phisalpha operator (written, read)
+    stream_bytes = 2 * (56 * 32 + 28 * 24 + 56 * 64 + 768) * 8.0 * (float(cnt[0]) + float(cnt[2]))
+    hbm_gbs = stream_bytes / (ksum[4] * 1e-3) / 1e9
     out = {
         "metric": "system-steps/s w/ grad (TRAPPIST-1 batch)", "value": value, "unit": "system-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "TRAPPIST-1 N=8 h=0.06 grad=true TransitTiming (BASELINE cfg 2)", "batch_per_gpu": nsys, "window_steps": window,
-                   "l2": "working set >> L2: operator stream %.1f GB/chunk, jac_step %.1f GB" % (28 * 152 * 8 * nsys * 8 / 1e9, nsys * 48 * 56 * 16 / 1e9),
+                   "chunk_steps": int(cnt[6]), "jac_launches": int(cnt[7]),
+                   "l2": "inputs larger than L2: operator stream %.1f GB + scalar stream %.1f GB per chunk, jac_step %.1f GB (L2 = 126 MB)" %
+                         ((28 * 152 + 768) * 8 * nsys * int(cnt[6]) / 1e9, 56 * 32 * 8 * nsys * int(cnt[6]) / 1e9, nsys * 48 * 56 * 16 / 1e9),
                    "parallelism": "systems sharded across GPUs, no collective"},
         "clocks": clocks, "gpu_launches": int(cnt[4]),
         "rates": {"main_steps_per_s": value, "step_equivalents_per_s": world * step_equiv / (ms_max * 1e-3),
@@ -301,19 +313,21 @@ def main():
                   "newton_iters_per_transit": float(cnt[1]) / max(1, int(cnt[3]))},
         "kernel_ms": {names[k]: float(ksum[k]) for k in range(3)} | {"phi_dense_kernel": float(ksum[5]), "pair_op_kernel": float(ksum[6]), "other": float(ksum[3]), "total": float(ksum[4])},
         "roofline": {"bound": "fp64", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "flops": "canonical (SURVEY 8d): F_jac(8)=%d per Jacobian step, F_scalar(8)=%d per trajectory step" %
+                     "traffic": traffic, "traffic_note": "dram read+write bytes per launch: ncu-measured bytes per Jacobian step x steps per launch",
+                     "flops": "canonical (SURVEY 8d): F_jac(8)=%d per Jacobian step, F_scalar(8)=%d per trajectory step" %
                      (f_jac(NBODY), f_grad(NBODY) - f_jac(NBODY)),
                      "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry; nominal 37.2)",
                      "path": {"achieved": path_achieved, "frac": path_achieved / peak if peak else None,
                               "note": "whole path: F_grad(8)=%d x step-equivalents / total device time" % f_grad(NBODY)},
-                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "note": "operator-stream write+read, algorithmic bytes"}},
-        "status_nonzero": int((status != 0).sum()),
+                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "note": "operator / scalar streams written once and read once, algorithmic bytes over total device time"}},
+        "status_bits": {"nonfinite": int((status & 1 != 0).sum()), "transit_itmax": int((status & 2 != 0).sum()),
+                        "event_overflow": int((status & 4 != 0).sum()), "ntt_overflow": int((status & 8 != 0).sum())},
     }
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns = cores * 2
+        ns = cores * args.ref_systems_per_core
         rate, dt, r = cpu_run(ns, args.ref_window, cores, x, v, m, jac_init)
         out["cpu_baseline"] = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
                                "sample": "%d systems x %d steps (%.1f s), oracle -O3 build, one system per thread" % (ns, args.ref_window, dt)}

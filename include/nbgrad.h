@@ -109,7 +109,8 @@ int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, c
 /* ---- instrumentation ---------------------------------------------------------------------------------------------
  * Counters accumulated since plan creation / nbg_counters_reset:
  *  c[0] main-loop system-steps, c[1] findtransit Newton step-equivalents, c[2] final (Jacobian) transit steps,
- *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main + transit).
+ *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main + transit),
+ *  c[6] steps per chunk of the last call (operator-stream budget), c[7] Jacobian-kernel launches.
  * nbg_last_timings: device milliseconds (CUDA events on the plan's stream) spent in the last compute call in the
  *  trajectory kernel [0], transit-refinement kernel [1], Jacobian kernel [2], everything else [3]; [4] = total;
  *  [5] = dense phisalpha-operator kernel; [6] = pair-operator kernel (split path); [7] reserved (0). */

@@ -773,6 +773,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       tm.end();
     }
     if (grad) {
+      p->counters_host[6] = (unsigned long long)S;
+      p->counters_host[7] += 1;
       tm.begin(2);
       if (use_rx) {
         const int32_t* evl = detect ? evlist : nullptr;
