@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--ref-systems-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-slices", type=int, default=1, help="slices (plans + host threads) of the end-to-end arm")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,37 +238,69 @@ def main():
     main_steps = nsys * window * args.steps
     value = world * main_steps / (ms_max * 1e-3)
 
-    # ---- end-to-end arm: one-shot C-ABI call, host buffers ----
+    # ---- end-to-end arm: the one-shot C-ABI call with HOST (pinned) buffers ----
+    # The batch is cut into `--e2e-slices` slices, each with its own plan (= its own stream) driven by its own host thread --
+    # "different plans may be used from different threads" (include/nbgrad.h) -- so one slice's H2D/D2H copies overlap the
+    # other slices' kernels.  Every byte of input and output crosses PCIe inside the timed region, every step.
     e2e = None
     if not args.no_e2e:
-        px, ax = pin(x); pv, av = pin(v); pm, am = pin(m)
-        pj, aj = pin(jac_init.transpose(0, 2, 1))
-        ptt, att = pin(np.zeros((nsys, RT))); pc, ac = pin(np.zeros((nsys, NBODY), dtype=np.int64))
-        pd, ad = pin(np.zeros((nsys, RT, M))); pe, ae = pin(np.zeros((nsys, RT, M)))
-        pxo, axo = pin(np.zeros_like(x)); pvo, avo = pin(np.zeros_like(v))
-        h2d = ax.nbytes + av.nbytes + am.nbytes + aj.nbytes
-        d2h = att.nbytes + ac.nbytes + ad.nbytes + ae.nbytes + axo.nbytes + avo.nbytes
+        _lib.check(L.nbg_plan_destroy(plan))
+        plan = None
+        K = max(1, min(args.e2e_slices, nsys))
+        free_b, _tot = torch.cuda.mem_get_info()
+        bounds = [nb.shard_range(nsys, k, K) for k in range(K)]
+        slices = []
+        h2d = d2h = 0
+        for lo, hi in bounds:
+            ns = hi - lo
+            pl = C.c_void_p()
+            _lib.check(L.nbg_plan_create(C.byref(pl), C.c_int32(NBODY), C.c_int64(ns), C.c_int32(local), C.c_int64(int(free_b // (5 * K)))))
+            bufs = dict(x=pin(x[lo:hi])[1], v=pin(v[lo:hi])[1], m=pin(m[lo:hi])[1], j=pin(jac_init[lo:hi].transpose(0, 2, 1))[1],
+                        tt=pin(np.zeros((ns, RT)))[1], c=pin(np.zeros((ns, NBODY), dtype=np.int64))[1], d=pin(np.zeros((ns, RT, M)))[1],
+                        e=pin(np.zeros((ns, RT, M)))[1], xo=pin(np.zeros((ns, NBODY, 3)))[1], vo=pin(np.zeros((ns, NBODY, 3)))[1])
+            h2d += sum(bufs[k].nbytes for k in ("x", "v", "m", "j"))
+            d2h += sum(bufs[k].nbytes for k in ("tt", "c", "d", "e", "xo", "vo"))
+            slices.append((pl, bufs))
 
-        def step_e2e():
-            _lib.check(L.nbg_transit_timing(plan, ptr(ax), ptr(av), ptr(am), None, C.c_double(T0), C.c_double(H), C.c_double(tmaxw), C.c_int32(0),
-                                            ptr(ntt), C.c_int32(0), C.c_int32(1), ptr(aj), ptr(att), ptr(ac), ptr(ad), ptr(ae), ptr(axo), ptr(avo),
-                                            None, None, None, None, None, None, None))
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ee0.record(stream)
-        for _ in range(args.steps):
-            step_e2e()
-        ee1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ems = max(ee0.elapsed_time(ee1), wall * 1e3)  # blocking host call: wall clock includes the host-side copies
-        t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)
+        def step_e2e(pl, B):
+            _lib.check(L.nbg_transit_timing(pl, ptr(B["x"]), ptr(B["v"]), ptr(B["m"]), None, C.c_double(T0), C.c_double(H), C.c_double(tmaxw),
+                                            C.c_int32(0), ptr(ntt), C.c_int32(0), C.c_int32(1), ptr(B["j"]), ptr(B["tt"]), ptr(B["c"]), ptr(B["d"]),
+                                            ptr(B["e"]), ptr(B["xo"]), ptr(B["vo"]), None, None, None, None, None, None, None))
+
+        gate = threading.Barrier(K + 1)
+        errs = []
+
+        def worker(pl, B):
+            try:
+                torch.cuda.set_device(local)
+                step_e2e(pl, B)          # warm-up (allocations inside the plan)
+                gate.wait()
+                for _ in range(args.steps):
+                    step_e2e(pl, B)
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+                gate.abort()
+
+        threads = [threading.Thread(target=worker, args=sl) for sl in slices]
+        [t.start() for t in threads]
+        try:
+            gate.wait()
+        except threading.BrokenBarrierError:
+            pass
+        barrier_t0 = time.perf_counter()
+        [t.join() for t in threads]
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - barrier_t0
+        if errs:
+            raise errs[0]
+        t2 = torch.tensor([wall * 1e3], device="cuda", dtype=torch.float64)   # blocking host calls: wall clock is the end-to-end time
         if dist is not None:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * main_steps / (float(t2.item()) * 1e-3), "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "transits_checked": int(ac.sum())}
+               "d2h_bytes_per_step": int(d2h), "slices": K, "transits_checked": int(sum(B["c"].sum() for _, B in slices)),
+               "timing": "host wall clock around %d blocking nbg_transit_timing calls per slice, max over ranks" % args.steps}
+        for pl, _B in slices:
+            L.nbg_plan_destroy(pl)
 
     if rank != 0:
         if dist is not None:
@@ -332,7 +365,8 @@ def main():
         out["cpu_baseline"] = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
                                "sample": "%d systems x %d steps (%.1f s), oracle -O3 build, one system per thread" % (ns, args.ref_window, dt)}
     print(json.dumps(out))
-    L.nbg_plan_destroy(plan)
+    if plan is not None:
+        L.nbg_plan_destroy(plan)
     if dist is not None:
         dist.destroy_process_group()
 

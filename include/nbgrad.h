@@ -24,8 +24,10 @@
  *  - the caller owns every host pointer; the library owns device memory inside the plan and keeps no host
  *    pointer after a call returns.  Calls on one plan must be serialised by the caller; different plans may be
  *    used from different threads.  Calls block until results are in the host buffers.
- *  - s.pair (Integrator.jl:91) must be all-false (the reference default; nothing in src/ sets it): `pair`
- *    arguments are accepted as NULL or all-zero, anything else returns NBG_ERR_UNSUPPORTED.
+ *  - s.pair (Integrator.jl:91; all-false by default, nothing in src/ sets it): `pair` is Julia's N x N Bool matrix
+ *    (entry [i,j] at i + N*j, one byte each; only i < j is read, as in the reference) or NULL = all-false.  Flagged pairs
+ *    get kickfast!/phic! instead of Kepler drifts (ahl21.jl:337-552); supported for nbody <= 8, else NBG_ERR_UNSUPPORTED.
+ *    One pair matrix applies to every system of the batch.
  *  - there is no CPU fallback: without a CUDA device every compute call returns NBG_ERR_NO_DEVICE.
  */
 #ifndef NBGRAD_H
@@ -65,6 +67,8 @@ int32_t nbg_plan_destroy(nbg_plan* plan);
  * nbg_set_state uploads x, v, m (required) and optionally xerror, verror, jac_step, jac_error, dqdt
  * (NULL = the State(ic) defaults: zeros, jac_step = I; Integrator.jl:82-103), and sets s.t = t0 for all systems.
  * nbg_get_state downloads whatever is non-NULL. */
+/* s.pair for the resident-state calls (the one-shot calls take it as an argument); sticky until changed. */
+int32_t nbg_set_pair(nbg_plan* plan, const uint8_t* pair);
 int32_t nbg_set_state(nbg_plan* plan, const double* x, const double* v, const double* m, double t0, const double* xerror,
                       const double* verror, const double* jac_step, const double* jac_error, const double* dqdt);
 int32_t nbg_get_state(nbg_plan* plan, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error,

@@ -67,7 +67,7 @@ struct TransitOut {
 template <bool GRAD, int EMIT>
 __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, double* scal, int detect, int ti,
                                                    double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
-                                                   int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err) {
+                                                   int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err, uint32_t kmask) {
   const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= nsys) return;
   const size_t ld = T.ld;
@@ -83,11 +83,11 @@ __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel
   if (detect) for (int i = 0; i < n; ++i) { gs[i] = T.gsave[i * ld + sys]; cnt[i] = T.count[i * ld + sys]; }
   double tnow = T.t[sys], terr = tkahan_err ? tkahan_err[sys] : 0.0;
   uint32_t st = 0;
-  const size_t sf = step_fields(n);
+  const size_t sf = step_fields(n, kmask != 0u);
   for (int s = 0; s < nsteps; ++s) {
     Emit em{EMIT ? stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys) : nullptr, TILE, (size_t)(sys % TILE),
             EMIT == 2 ? scal + tile_offset((size_t)2 * npairs(n) * SCF, ld / TILE, (size_t)s, (size_t)sys) : nullptr};
-    ahl21_step<GRAD, EMIT>(b, dq, n, h, em);
+    ahl21_step<GRAD, EMIT>(b, dq, n, h, em, kmask);
     if (time_mode_kahan) ksum(tnow, terr, h);                      // (intr)(s,N): Integrator.jl:229
     else tnow = t0 + ((double)(istep0 + s + 1) * h);               // Transits.jl:161
     if (detect) {
@@ -158,7 +158,7 @@ __global__ void gsave_init_kernel(TrajArrays T, int n, long nsys, int ti) {
 // ------------------------------------------------------------------------------------------------------------------
 // findtransit! (timing.jl:31-110).  One thread per queued transit.
 template <bool GRAD>
-__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters) {
+__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(*Q.n, Q.cap);
   if (e >= nq) return;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
     tt2 = tt1;
     tt1 = dt0;
     b = b0;
-    ahl21_step<true, 0>(b, dq, n, dt0, none);
+    ahl21_step<true, 0>(b, dq, n, dt0, none, kmask);
     const double gs = gsky(b, ti, j);
     const double gd = gdot(b, dq, ti, j);
     const double dt = -gs / gd;
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   uint32_t st = (iter >= 20) ? NBG_ST_TRANSIT_ITMAX : 0u;
   if (GRAD) {
     b = b0;
-    Emit em{Q.stream + tile_offset(step_fields(n), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
-    ahl21_step<true, 1>(b, dq, n, dt0, em);
+    Emit em{Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
+    ahl21_step<true, 1>(b, dq, n, dt0, em, kmask);
   }
   const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
   const double dvx = b.v[3 * j] - b.v[3 * ti], dvy = b.v[3 * j + 1] - b.v[3 * ti + 1];
@@ -280,13 +280,17 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 // register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>()>
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
 __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
-                  int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O) {
+                  int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
+                  uint32_t kmask) {
   extern __shared__ __align__(16) double smrx[];
-  constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + PF) + 12 * N * N /* stream */, SB = 2 * P * KF + 12 * N * N /* staged */,
-                G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = rx_warps(N) * 32;
+  constexpr int NS = KICK ? 3 : 1;  // dense operators per step (nbg_kicks.cuh)
+  constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + NS * PF) + NS * 12 * N * N /* stream */,
+                SB = 2 * P * KF + NS * 12 * N * N /* staged */, G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + NS * PF) / 4, G1 = NS * 3 * N * N,
+                NT = rx_warps(N) * 32;
+  double* const hold = smrx + 2 * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
   const long sys = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, c = warp * 16 + (lane & 15);
   const bool valid = c < M;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       __syncthreads();
       h2 = 0.5 * Q.hdr[7 * cap + slot];
     }
-    rx_step<N, U, SYNC>(S, cur, h2, half, c);
+    rx_step<N, U, SYNC, KICK>(S, cur, h2, half, c, kmask, hold, NT);
     if (in_event) {
       // dtbvdq! (timing.jl:155-194): rows x0,x1 (x half) and v0,v1 (v half) of occultor ev_i and transited body ti
       double d0 = 0.0, d1 = 0.0;
@@ -428,42 +432,60 @@ __global__ void __launch_bounds__(128, 2) pair_op_kernel(const double* __restric
 // lanes of a warp are consecutive systems, so every record read and every output write is a coalesced run of sectors.
 template <int N>
 __global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(double* __restrict__ base, size_t ntiles, long nitems,
-                                                                         const int32_t* __restrict__ nitems_dev) {
+                                                                         const int32_t* __restrict__ nitems_dev, int kicked) {
   const long idx = (long)blockIdx.x * 32 + threadIdx.x;
   const long nv = nitems_dev ? min((long)*nitems_dev, nitems) : nitems;
   if (idx >= nv) return;
-  phi_dense_rows<N>(base + tile_offset(step_fields(N), ntiles, blockIdx.y, (size_t)idx), TILE, (size_t)threadIdx.x, (int)threadIdx.y);
+  double* blk = base + tile_offset(step_fields(N, kicked != 0), ntiles, blockIdx.y, (size_t)idx);
+  if (!kicked) phi_dense_rows<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y);
+  else phi_dense_rows_kicked<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y, phi_rec_offset(N, blockIdx.z), phi_dense_offset(N, true, blockIdx.z));
 }
 // main steps: ntiles = ld / 32, nsteps steps; queued transits: ntiles = 0 (one "step"), nitems_dev = device count of queued transits
-int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long nitems, const int32_t* nitems_dev, int nsteps) {
+int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long nitems, const int32_t* nitems_dev, int nsteps, bool kicked = false) {
   if (nitems <= 0 || nsteps <= 0) return 0;
-  const dim3 grid((unsigned)((nitems + 31) / 32), (unsigned)nsteps), block(32, n);
+  const dim3 grid((unsigned)((nitems + 31) / 32), (unsigned)nsteps, kicked ? 3u : 1u), block(32, n);
+  const int kf = kicked ? 1 : 0;
   switch (n) {
-    case 2: phi_dense_kernel<2><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
-    case 3: phi_dense_kernel<3><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
-    case 4: phi_dense_kernel<4><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
-    case 5: phi_dense_kernel<5><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
-    case 6: phi_dense_kernel<6><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
-    case 7: phi_dense_kernel<7><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
-    case 8: phi_dense_kernel<8><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev); break;
+    case 2: phi_dense_kernel<2><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 3: phi_dense_kernel<3><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 4: phi_dense_kernel<4><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 5: phi_dense_kernel<5><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 6: phi_dense_kernel<6><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 7: phi_dense_kernel<7><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 8: phi_dense_kernel<8><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     default: return -1;
   }
   return 0;
 }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>()>
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
-                  const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O) {
-  constexpr int P = N * (N - 1) / 2, SB = 2 * P * KF + 12 * N * N;
-  const size_t smem = (size_t)2 * SB * 8;
+                  const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
+  constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
+  const size_t smem = ((size_t)2 * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0)) * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
-  jac_rx_kernel<N, U, SYNC, MB><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O);
+  jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O,
+                                                                                     kmask);
   return 0;
+}
+// fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
+int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
+                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask) {
+  switch (n) {
+    case 2: return launch_jac_rx<2, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 3: return launch_jac_rx<3, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 4: return launch_jac_rx<4, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 5: return launch_jac_rx<5, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 6: return launch_jac_rx<6, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 7: return launch_jac_rx<7, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 8: return launch_jac_rx<8, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+  }
+  return -1;
 }
 
 // dtdelements = dtdq0 . jac_init  (calc_dtdelements!, timing.jl:112-138).  One block per (system, record tile).
@@ -582,6 +604,8 @@ struct nbg_plan {
   size_t ld = 0;
   int64_t stream_budget = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // uploads that overlap the stepping (jac_init)
+  cudaEvent_t copy_done = nullptr;
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
   DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
@@ -589,6 +613,7 @@ struct nbg_plan {
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
   DevBuf stage[8];  // staging for host<->device conversions
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true;
+  uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
@@ -658,7 +683,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   const int n = p->n;
   const long nsys = p->nsys;
   const size_t ld = p->ld;
-  const size_t sf = step_fields(n);
+  const bool kicks = p->kmask != 0u;
+  const size_t sf = step_fields(n, kicks);
   const size_t jsz = (size_t)6 * n * 7 * n;
   // chunk length from the stream budget
   size_t per_step = sf * ld * 8;
@@ -700,7 +726,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     const size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
     if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
-  const bool use_rx = n <= 8 && !p->force_generic_jac;
+  const bool use_rx = n <= 8 && (!p->force_generic_jac || kicks);
+  if (kicks && n > 8) return fail(NBG_ERR_UNSUPPORTED, "fast-kick pairs (s.pair) are supported for nbody <= 8");
   const int tpb = 128;
   const unsigned gridA = (unsigned)((nsys + tpb - 1) / tpb);
   const int tps = 32 * ((7 * n + 31) / 32);
@@ -719,7 +746,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     tm.begin(0);
     double* tkerr = kahan_time ? p->bterr.as<double>() : nullptr;
     int s_split = 0;  // steps of this chunk whose Kepler records come from pair_op_kernel (split path)
-    if (grad && p->split_traj) {
+    if (grad && p->split_traj && !kicks) {
       // dq/dh restarts from zero every step (ahl21.jl:9), so only the last step of the integration needs it: that step
       // also evaluates the pair Jacobians in the trajectory thread (GRAD = true).  Every step's operator records come from
       // pair_op_kernel, so jac_step does not depend on how the integration is cut into chunks or calls.
@@ -728,29 +755,29 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       s_split = s;
       if (s_light > 0)
         traj_kernel<false, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s_light, p->bstream.as<double>(), p->bscal.as<double>(), detect, ti, t0,
-                                                          done, h_intr, p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr);
+                                                          done, h_intr, p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
       if (s_light < s) {
         const size_t o = (size_t)s_light;
         traj_kernel<true, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s - s_light, p->bstream.as<double>() + o * sf * ld,
                                                          p->bscal.as<double>() + o * 2 * npairs(n) * SCF * ld, detect, ti, t0, done + s_light, h_intr,
                                                          p->bntt.as<int32_t>(), Q, evlist ? evlist + o * n * ld : nullptr,
-                                                         evmask ? evmask + o * ld : nullptr, kahan_time, tkerr);
+                                                         evmask ? evmask + o * ld : nullptr, kahan_time, tkerr, p->kmask);
         if (s_light > 0) p->launches++;
       }
     } else if (grad) {
       traj_kernel<true, 1><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
-                                                       p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr);
+                                                       p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
     } else {
       traj_kernel<false, 0><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
-                                                         Q, evlist, evmask, kahan_time, tkerr);
+                                                         Q, evlist, evmask, kahan_time, tkerr, p->kmask);
     }
     tm.end();
     p->launches++;
     if (detect) {
       tm.begin(1);
       const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
-      if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount);
-      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount);
+      if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
+      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
       tm.end();
       p->launches++;
     }
@@ -764,10 +791,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     }
     if (grad && use_rx) {
       tm.begin(5);
-      if (launch_phi_dense(p->stream, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      if (launch_phi_dense(p->stream, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
       p->launches++;
       if (detect) {
-        if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+        if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
         p->launches++;
       }
       tm.end();
@@ -782,7 +809,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>(), *Jb = p->bJbak.as<double>();
         const double* strm = p->bstream.as<double>();
         int rc = 0;
-        switch (n) {
+        if (kicks) rc = launch_jac_rx_kicked(n, p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, p->kmask);
+        else switch (n) {
           case 2: rc = launch_jac_rx<2, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 3: rc = launch_jac_rx<3, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 4: rc = launch_jac_rx<4, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
@@ -825,10 +853,18 @@ int ensure_jac(nbg_plan* p) {
   return 0;
 }
 
-int check_pair(const uint8_t* pair, int n) {
+// s.pair (Integrator.jl:91): Julia column-major N x N Bool, entry [i,j] at i + n*j; the reference only reads i < j
+int pair_mask(const uint8_t* pair, int n, uint32_t* mask) {
+  *mask = 0;
   if (!pair) return 0;
-  for (int q = 0; q < n * n; ++q)
-    if (pair[q]) return fail(NBG_ERR_UNSUPPORTED, "s.pair must be all-false (kickfast!/phic! pairs are not built yet)");
+  bool any = false;
+  for (int i = 0; i < n - 1; ++i)
+    for (int j = i + 1; j < n; ++j)
+      if (pair[i + n * j]) {
+        any = true;
+        if (n <= 8) *mask |= 1u << (i * n - i * (i + 1) / 2 + (j - i - 1));
+      }
+  if (any && n > 8) return fail(NBG_ERR_UNSUPPORTED, "fast-kick pairs (s.pair) are supported for nbody <= 8");
   return 0;
 }
 
@@ -857,6 +893,8 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   p->n = nbody; p->nsys = nsys; p->device = device;
   p->ld = (size_t)((nsys + 31) / 32 * 32);
   CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
   if (stream_budget_bytes <= 0) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
@@ -882,7 +920,17 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   for (auto* b : all) b->release();
   for (auto& b : p->stage) b.release();
   cudaStreamDestroy(p->stream);
+  cudaStreamDestroy(p->copy_stream);
+  cudaEventDestroy(p->copy_done);
   delete p;
+  return NBG_OK;
+}
+
+int32_t nbg_set_pair(nbg_plan* p, const uint8_t* pair) {
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  uint32_t mask = 0;
+  if (int r = pair_mask(pair, p->n, &mask)) return r;
+  p->kmask = mask;
   return NBG_OK;
 }
 
@@ -1019,7 +1067,7 @@ int32_t nbg_integrate(nbg_plan* p, const double* x0, const double* v0, const dou
                       double h_last, int32_t grad, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error,
                       double* dqdt, uint32_t* status) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
-  if (int r = check_pair(pair, p->n)) return r;
+  if (int r = nbg_set_pair(p, pair)) return r;
   if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
   if (int r = nbg_integrate_resident(p, h, nsteps, h_last, grad, 0, 0.0)) return r;
   return nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, nullptr, status);
@@ -1064,16 +1112,22 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   const int tpb = 128;
   gsave_init_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T, n, (long)nsys, ti);
   p->launches++;
+  // jac_init (M^2 doubles per system, the bulk of the input bytes) is uploaded on a second stream while the steps run
+  const bool want_dtde = grad && jac_init;
+  if (want_dtde) {
+    if (p->bjinit.ensure(nsys * M * M * 8) || p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
+      return fail(NBG_ERR_NOMEM, "dtdelements allocation failed");
+    CK(cudaMemcpyAsync(p->bjinit.p, jac_init, nsys * M * M * 8, cudaMemcpyHostToDevice, p->copy_stream));
+    CK(cudaMemsetAsync(p->bdtde.p, 0, nsys * RT * M * C * 8, p->copy_stream));
+    CK(cudaEventRecord(p->copy_done, p->copy_stream));
+  }
   double rate = nsteps > 0 ? (double)RT / (double)nsteps : 1.0;
-  if (int r = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate)) return r;
+  if (int r = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate)) { cudaStreamSynchronize(p->copy_stream); return r; }
   p->have_transit = true;
   p->transit_grad = grad != 0;
   p->have_dtde = false;
-  if (grad && jac_init) {
-    if (p->bjinit.ensure(nsys * M * M * 8) || p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
-      return fail(NBG_ERR_NOMEM, "dtdelements allocation failed");
-    CK(cudaMemcpyAsync(p->bjinit.p, jac_init, nsys * M * M * 8, cudaMemcpyHostToDevice, p->stream));
-    CK(cudaMemsetAsync(p->bdtde.p, 0, nsys * RT * M * C * 8, p->stream));
+  if (want_dtde) {
+    CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
     CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * M * 8)));
     dtdelements_kernel<<<(unsigned)nsys, 256, M * M * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
                                                                      p->bcount.as<int32_t>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), n, p->ld, RT,
@@ -1111,7 +1165,7 @@ int32_t nbg_transit_timing(nbg_plan* p, const double* x0, const double* v0, cons
                            double* dtdq0, double* dtdelements, double* x, double* v, double* xerror, double* verror, double* jac_step,
                            double* jac_error, double* dqdt, double* t, uint32_t* status) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
-  if (int r = check_pair(pair, p->n)) return r;
+  if (int r = nbg_set_pair(p, pair)) return r;
   if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
   if (int r = nbg_transit_timing_resident(p, h, tmax, ti, ntt_body, mode, grad, jac_init)) return r;
   if (int r = nbg_transit_fetch(p, tt, count, dtdq0, dtdelements)) return r;

@@ -15,7 +15,7 @@
 // are zero, ahl21.jl:735-750; jac_phi and the drift never touch them), so only 6N rows are stored and a mass
 // COLUMN of an operator contributes only to the thread that owns column 7p+6.
 #pragma once
-#include "nbg_step.cuh"
+#include "nbg_kicks.cuh"
 
 namespace nbg {
 

@@ -249,10 +249,124 @@ template <int N> __device__ __forceinline__ void phi_dense_rows(double* __restri
   }
 }
 
+// The same expansion with fast-kick pairs (nbg_kicks.cuh): records carry a class (the accelerations a^c only sum pairs of the
+// same class) and a direct-kick coefficient kappa.  rec_off / out_off: field offsets of the record set and of its dense block.
+template <int N> __device__ __forceinline__ void phi_dense_rows_kicked(double* __restrict__ blk, size_t stride, size_t idx, int i, size_t rec_off,
+                                                                         size_t out_off) {
+  const double* __restrict__ PH = blk + ((rec_off / 4) * stride + idx) * 4;
+  double* __restrict__ OUT = blk + ((out_off / 4) * stride + idx) * 4;
+  const size_t gs = stride * 4;
+  auto grp = [&](int p, int g) { return reinterpret_cast<const double2*>(PH + (size_t)(p * (PF / 4) + g) * gs); };
+  struct TG { double T[6], gam[3], ma, mb; int cls; };
+  auto load_tg = [&](int a, int b) {
+    const int p = rx_pair_index(N, a < b ? a : b, a < b ? b : a);
+    const double2 u = __ldg(grp(p, 0)), v = __ldg(grp(p, 0) + 1), e = __ldg(grp(p, 1)), f = __ldg(grp(p, 1) + 1), z = __ldg(grp(p, 5) + 1);
+    const double r0 = u.x, r1 = u.y, r2 = v.x, g3 = v.y, g5 = e.x, mi = e.y, mj = f.x;
+    const double sg = a < b ? 1.0 : -1.0;
+    TG o;
+    o.T[0] = g3 - g5 * r0 * r0; o.T[1] = -g5 * r0 * r1; o.T[2] = -g5 * r0 * r2;
+    o.T[3] = g3 - g5 * r1 * r1; o.T[4] = -g5 * r1 * r2; o.T[5] = g3 - g5 * r2 * r2;
+    o.gam[0] = sg * g3 * r0; o.gam[1] = sg * g3 * r1; o.gam[2] = sg * g3 * r2;
+    o.ma = a < b ? mi : mj; o.mb = a < b ? mj : mi;
+    o.cls = z.y != 0.0 ? 1 : 0;
+    return o;
+  };
+#pragma unroll 1
+  for (int d = 0; d < N; ++d) {
+    double diag[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      if (l == d) continue;
+      const TG t = load_tg(d, l);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        diag[0][q] = fma(t.cls ? 0.0 : -t.mb, t.T[q], diag[0][q]);
+        diag[1][q] = fma(t.cls ? -t.mb : 0.0, t.T[q], diag[1][q]);
+      }
+    }
+    // A^c[b][d]: x part (6) and mass part (3) of d a_b^c / d (x_d, m_d)
+    auto Aget = [&](int b, int c, double (&ax)[6], double (&am)[3]) {
+      if (b == d) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ax[q] = c ? diag[1][q] : diag[0][q];
+        am[0] = 0.0; am[1] = 0.0; am[2] = 0.0;
+      } else {
+        const TG t = load_tg(d, b);
+        const double on = t.cls == c ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ax[q] = on * t.ma * t.T[q];
+        am[0] = on * t.gam[0]; am[1] = on * t.gam[1]; am[2] = on * t.gam[2];
+      }
+    };
+    double acc[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[k][q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const int p = rx_pair_index(N, i < j ? i : j, i < j ? j : i);
+      const double2 a = __ldg(grp(p, 0)), b = __ldg(grp(p, 0) + 1), e = __ldg(grp(p, 1)), f = __ldg(grp(p, 1) + 1), g = __ldg(grp(p, 2)),
+                    z = __ldg(grp(p, 5) + 1);
+      const double r[3] = {a.x, a.y, b.x};
+      const double g3 = b.y, g5 = e.x, mj = i < j ? f.x : e.y, fac1 = f.y, rsq = g.x, us = g.y, kappa = z.x;
+      const int c = z.y != 0.0 ? 1 : 0;
+      const double sg = i < j ? 1.0 : -1.0;
+      double axi[6], ami[3], axj[6], amj[3];
+      Aget(i, c, axi, ami);
+      Aget(j, c, axj, amj);
+      double u[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) u[q] = axi[q] - axj[q];
+      const double col[4][3] = {{u[0], u[1], u[2]}, {u[1], u[3], u[4]}, {u[2], u[4], u[5]}, {ami[0] - amj[0], ami[1] - amj[1], ami[2] - amj[2]}};
+      double ev[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double ru = 3.0 * (r[0] * col[q][0] + r[1] * col[q][1] + r[2] * col[q][2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ev[q][k] = fac1 * (r[k] * ru - rsq * col[q][k]);
+      }
+      if (d == i || d == j) {
+        const double2 g1 = __ldg(grp(p, 2) + 1), h0 = __ldg(grp(p, 3)), h1 = __ldg(grp(p, 3) + 1), k0 = __ldg(grp(p, 4)), k1 = __ldg(grp(p, 4) + 1),
+                      l0 = __ldg(grp(p, 5));
+        const double F[3] = {g1.x, g1.y, h0.x};
+        const double Rm[9] = {h0.y, h1.x, h1.y, k0.x, k0.y, k1.x, k1.y, l0.x, l0.y};
+        const double T[9] = {g3 - g5 * r[0] * r[0], -g5 * r[0] * r[1], -g5 * r[0] * r[2], -g5 * r[1] * r[0], g3 - g5 * r[1] * r[1], -g5 * r[1] * r[2],
+                             -g5 * r[2] * r[0], -g5 * r[2] * r[1], g3 - g5 * r[2] * r[2]};
+        const double sr = d == i ? 1.0 : -1.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) ev[q][k] = fma(sr, Rm[3 * k + q] - kappa * T[3 * k + q], ev[q][k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ev[3][k] = fma(sg * us, r[k], ev[3][k]);
+        if (d == j) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc[k][3] += sg * (F[k] - kappa * g3 * r[k]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k][q] = fma(mj, ev[q][k], acc[k][q]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double2* o = reinterpret_cast<double2*>(OUT + (size_t)((3 * i + k) * N + d) * gs);
+      o[0] = make_double2(acc[k][0], acc[k][1]);
+      o[1] = make_double2(acc[k][2], acc[k][3]);
+    }
+  }
+}
+
 // jac_step (+)= jac_phi * jac_step with the dense operator W (layout of phi_dense_fields) staged in shared memory;
 // jv/je at offset OFF (position p holds body (OFF + p) mod N).  The x half multiplies the x rows of bodies 0..NA-1, the
 // v half (which receives them by shuffle) those of bodies NA..N-1, each into all 3N outputs; the v half adds the two.
-template <int N, int OFF> __device__ __forceinline__ void rx_phisalpha_dense(RxState<N>& S, const double* __restrict__ W, int half, int c) {
+// HOLD: instead of adding, park dv in hold[(3 b + k) * hs] (first kickfast!: jac_kick * jac_step is formed BEFORE drift_grad!
+// and added after it, ahl21.jl:16-23); rx_fold_add applies it.
+template <int N, int OFF, bool HOLD = false>
+__device__ __forceinline__ void rx_phisalpha_dense(RxState<N>& S, const double* __restrict__ W, int half, int c, double* hold = nullptr, int hs = 0) {
   constexpr int NA = (N + 1) / 2;
   double in[NA][3];
   static_for<0, NA>([&](auto Qc) {
@@ -295,9 +409,16 @@ template <int N, int OFF> __device__ __forceinline__ void rx_phisalpha_dense(RxS
       double dv = part + other;
       if (dm >= 0) dv += W[((3 * b + k) * N + dm) * 4 + 3];
       // comp_sum_matrix!(jac_step, jac_error, jac_phi * jac_step): v rows get dv, x rows a zero addend (fold)
-      ksum_m(S.jv[pos][k], S.je[pos][k], half == 1 ? dv : 0.0);
+      if (HOLD) hold[(3 * b + k) * hs] = dv;
+      else ksum_m(S.jv[pos][k], S.je[pos][k], half == 1 ? dv : 0.0);
     }
   });
+}
+template <int N> __device__ __forceinline__ void rx_fold_add(RxState<N>& S, const double* hold, int hs, int half) {  // offset 0
+#pragma unroll
+  for (int b = 0; b < N; ++b)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ksum_m(S.jv[b][k], S.je[b][k], half == 1 ? hold[(3 * b + k) * hs] : 0.0);
 }
 
 // ---- sweeps over pairs in blocks of U pivot bodies ---------------------------------------------------------------
@@ -352,24 +473,30 @@ template <int N, int U, bool SYNC = true> struct RxSweep {
   }
 };
 
-// one AHL21 Jacobian step from a staged operator block [2P Kepler records | dense phisalpha operator];
-// offset 0 (identity) on entry and exit.
-template <int N, int U, bool SYNC = true>
-__device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c) {
-  constexpr int P = N * (N - 1) / 2;
+// one AHL21 Jacobian step from a staged operator block [2P Kepler records | dense operators]; offset 0 on entry and exit.
+// KICK: fast-kick pairs present (kmask, nbg_kicks.cuh): three dense operators (kickfast!, phic!+phisalpha!, kickfast!), the
+// flagged pairs are skipped in the Kepler sweeps; hold/hs: per-thread scratch for the first kick (see rx_phisalpha_dense).
+template <int N, int U, bool SYNC = true, bool KICK = false>
+__device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c, uint32_t kmask = 0u,
+                                        double* hold = nullptr, int hs = 0) {
+  constexpr int P = N * (N - 1) / 2, DF = 12 * N * N;
   using SW = RxSweep<N, U, SYNC>;
   auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(S.je); };
   auto pair = [&](auto PA, auto PB, const double* R, int bi, int bj) {
-    rx_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, half, c, 7 * bi + 6, 7 * bj + 6);
+    if (!KICK || !((kmask >> rx_pair_index(N, bi, bj)) & 1u)) rx_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, half, c, 7 * bi + 6, 7 * bj + 6);
   };
+  const double* __restrict__ D = blk + 2 * P * KF;
+  if (KICK) rx_phisalpha_dense<N, 0, true>(S, D, half, c, hold, hs);
   rx_drift<N>(S, h2, half);
-  rx_fold<N>(S);
+  if (KICK) rx_fold_add<N>(S, hold, hs, half);
+  else rx_fold<N>(S);
   SW::asc(rotate, blk, KF, pair);                                          // offset 0 -> A1
-  rx_phisalpha_dense<N, SW::A1>(S, blk + 2 * P * KF, half, c);             // A1 -> A1
+  rx_phisalpha_dense<N, SW::A1>(S, D + (KICK ? DF : 0), half, c);         // A1 -> A1
   rotate(std::integral_constant<int, SW::KTOP * U - SW::A1>{});            // A1 -> KTOP*U
   SW::desc(rotate, blk + P * KF, KF, pair);                                // -> 0
   rx_drift<N>(S, h2, half);
-  rx_fold<N>(S);
+  if (KICK) rx_phisalpha_dense<N, 0>(S, D + 2 * DF, half, c);
+  else rx_fold<N>(S);
 }
 
 }  // namespace nbg

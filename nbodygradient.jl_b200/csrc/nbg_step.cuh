@@ -53,9 +53,15 @@ __host__ __device__ inline int npairs(int n) { return n * (n - 1) / 2; }
 // doubles per system per step in the operator stream: [2P Kepler records | P phisalpha records | dense phisalpha operator]
 // dense operator (written by phi_dense_kernel, read by the register-resident Jacobian kernel): element
 // ((3 i + k) N + d) 4 + p = d v_i[k] / d x_d[p] for p < 3, d v_i[k] / d m_d for p = 3.
+// With fast-kick pairs (s.pair not all-false) a step carries THREE sets of compact records and dense operators: first
+// kickfast!, phic!+phisalpha!, second kickfast! (nbg_kicks.cuh).
 __host__ __device__ inline size_t phi_dense_fields(int n) { return (size_t)12 * n * n; }
-__host__ __device__ inline size_t phi_dense_offset(int n) { return (size_t)npairs(n) * (2 * KF + PF); }
-__host__ __device__ inline size_t step_fields(int n) { return phi_dense_offset(n) + phi_dense_fields(n); }
+__host__ __device__ inline int phi_sets(bool kicked) { return kicked ? 3 : 1; }
+__host__ __device__ inline size_t phi_rec_offset(int n, int set) { return (size_t)npairs(n) * (2 * KF + set * PF); }
+__host__ __device__ inline size_t phi_dense_offset(int n, bool kicked = false, int set = 0) {
+  return (size_t)npairs(n) * (2 * KF + phi_sets(kicked) * PF) + set * phi_dense_fields(n);
+}
+__host__ __device__ inline size_t step_fields(int n, bool kicked = false) { return phi_dense_offset(n, kicked, phi_sets(kicked)); }
 
 struct Body {
   double x[3 * NMAX], v[3 * NMAX], xe[3 * NMAX], ve[3 * NMAX], m[NMAX];
@@ -352,64 +358,6 @@ __device__ __forceinline__ void phisalpha_section(Body& b, double* dq, int n, do
   if (GRAD) for (int i = 0; i < n; ++i)
 #pragma unroll
     for (int k = 0; k < 3; ++k) dq[6 * i + 3 + k] += dvacc[3 * i + k];
-}
-
-// dq: d(state)/dh, 6 entries per body (x then v); mass entries are identically zero and not stored.
-// em.base points at this step's region of the operator stream (used when EMIT).
-template <bool GRAD, int EMIT>
-__device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em) {
-  const double h2 = 0.5 * h;
-  const int P = npairs(n);
-  // fill!(s.dqdt,0); kickfast! (no kicked pairs); drift_grad!/drift!; dqdt[x] = v/2 + h2 dqdt[v]   (ahl21.jl:8-21)
-  for (int i = 0; i < n; ++i) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      ksum(b.x[3 * i + k], b.xe[3 * i + k], h2 * b.v[3 * i + k]);
-      if (GRAD) { dq[6 * i + k] = 0.5 * b.v[3 * i + k]; dq[6 * i + 3 + k] = 0.0; }
-    }
-  }
-  int rec = 0;
-  for (int i = 0; i < n - 1; ++i) {
-    BodyRegs bi, bj, bn;
-    load_body<GRAD>(b, dq, i, bi);
-    load_body<GRAD>(b, dq, i + 1, bn);
-    for (int j = i + 1; j < n; ++j, ++rec) {
-      bj = bn;
-      if (j + 1 < n) load_body<GRAD>(b, dq, j + 1, bn);  // in flight while pair (i, j) is solved
-      pair_section<GRAD, EMIT>(bi, bj, h2, true, em, (size_t)rec * KF);
-      store_body<GRAD>(b, dq, j, bj);
-    }
-    store_body<GRAD>(b, dq, i, bi);
-  }
-  phisalpha_section<GRAD, EMIT>(b, dq, n, h, em, (size_t)2 * P * KF);
-  for (int i = n - 2; i >= 0; --i) {
-    BodyRegs bi, bj, bn;
-    load_body<GRAD>(b, dq, i, bi);
-    load_body<GRAD>(b, dq, n - 1, bn);
-    for (int j = n - 1; j >= i + 1; --j, ++rec) {
-      bj = bn;
-      if (j - 1 >= i + 1) load_body<GRAD>(b, dq, j - 1, bn);
-      pair_section<GRAD, EMIT>(bi, bj, h2, false, em, (size_t)rec * KF);
-      store_body<GRAD>(b, dq, j, bj);
-    }
-    store_body<GRAD>(b, dq, i, bi);
-  }
-  for (int i = 0; i < n; ++i) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      ksum(b.x[3 * i + k], b.xe[3 * i + k], h2 * b.v[3 * i + k]);
-      if (GRAD) dq[6 * i + k] += 0.5 * b.v[3 * i + k] + h2 * dq[6 * i + 3 + k];
-    }
-  }
-}
-
-// timing.jl:141-150  g!, gd!   (i = transited body, j = occultor)
-__device__ __forceinline__ double gsky(const Body& b, int i, int j) {
-  return (b.x[3 * j] - b.x[3 * i]) * (b.v[3 * j] - b.v[3 * i]) + (b.x[3 * j + 1] - b.x[3 * i + 1]) * (b.v[3 * j + 1] - b.v[3 * i + 1]);
-}
-__device__ __forceinline__ double gdot(const Body& b, const double* dq, int i, int j) {
-  return ((b.x[3 * j] - b.x[3 * i]) * (dq[6 * j + 3] - dq[6 * i + 3]) + (b.x[3 * j + 1] - b.x[3 * i + 1]) * (dq[6 * j + 4] - dq[6 * i + 4]) +
-          (b.v[3 * j] - b.v[3 * i]) * (dq[6 * j] - dq[6 * i]) + (b.v[3 * j + 1] - b.v[3 * i + 1]) * (dq[6 * j + 1] - dq[6 * i + 1]));
 }
 
 }  // namespace nbg

@@ -90,9 +90,9 @@ class State:
 
     # -- device transfer helpers
     def _upload(self, plan, with_jac):
-        if self.pair.any():
-            raise _lib.NbgError("NBG_ERR_UNSUPPORTED: s.pair must be all-false (kickfast!/phic! pairs are not built yet)")
         L = _lib.lib()
+        pr = np.asfortranarray(self.pair.astype(np.uint8))  # Julia layout: [i,j] at i + n*j
+        check(L.nbg_set_pair(plan, ptr(pr) if pr.any() else None))
         self._m_c = np.ascontiguousarray(self.m, dtype=np.float64)
         js = np.ascontiguousarray(self.jac_step.transpose(0, 2, 1)) if with_jac else None
         je = np.ascontiguousarray(self.jac_error.transpose(0, 2, 1)) if with_jac else None

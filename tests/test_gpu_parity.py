@@ -242,10 +242,57 @@ def test_outer_solar_system_nograd_energy(nb, oracle):
         assert np.linalg.norm(L1 - L0) / np.linalg.norm(L0) <= 1.1 * np.linalg.norm(Lo - L0) / np.linalg.norm(L0) + 1e-13
 
 
+@pytest.mark.parametrize("n,kick", [(3, [(1, 2)]), (5, [(1, 2), (3, 4)]), (8, [(1, 2), (1, 3), (2, 3), (6, 7)])])
+def test_fast_kick_pairs(nb, oracle, elements, n, kick):
+    # s.pair set by hand as in test/test_kickfast.jl:24-31 / test_phic.jl:25-31: flagged pairs get kickfast!/phic! instead of Kepler
+    # drifts (ahl21.jl:337-552).  State, Jacobian and dq/dh against the oracle, grad and no-grad, forward and backward.
+    el = elements[:n].copy(); el[1:, 0] *= 30
+    x, v, _ = oracle.init_nbody(el, 7257.0)
+    if n == 3:
+        x, v = tilt(x, v)
+    pair = np.zeros((n, n), dtype=bool)
+    for i, j in kick:
+        pair[i, j] = True
+    for h, nsteps, grad in ((0.05, 25, True), (-0.03, 7, True), (0.05, 25, False)):
+        so = oracle.new_state(x, v, el[:, 0], 7257.0); so["pair"] = pair
+        oracle.integrate(so, h, nsteps=nsteps, grad=grad)
+        s = nb.State(cartesian_ic(nb, x, v, el[:, 0], 7257.0)); s.pair[...] = pair
+        nb.Integrator(abs(h), 10.0)(s, nsteps if h > 0 else -nsteps, grad=grad)
+        assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+        if grad:
+            assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+            assert rel(s.dqdt[0], so["dqdt"]) < TOL
+    # and it is not the default map
+    s0 = nb.State(cartesian_ic(nb, x, v, el[:, 0], 7257.0))
+    nb.Integrator(0.05, 10.0)(s0, 25, grad=False)
+    assert rel(s0.x[0], so["x"]) > 1e-9
+
+
+def test_fast_kick_pairs_transit_timing(nb, oracle, elements):
+    n, t0, h, tmax = 4, 7257.0, 0.05, 12.0
+    el = elements[:n].copy()
+    pair = np.zeros((n, n), dtype=bool); pair[2, 3] = True
+    x, v, jac = oracle.init_nbody(el, t0)
+    so = oracle.new_state(x, v, el[:, 0], t0); so["pair"] = pair
+    ic = nb.ElementsIC(t0, n, el)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    s.pair[...] = pair
+    r = oracle.transit_timing(so, h, tmax, tt.ntt, grad=True, jac_init=jac)
+    nb.Integrator(h, tmax)(s, tt)
+    _cmp_tt(tt.tt[0], tt.count[0], r)
+    assert r["count"].sum() > 10
+    assert rel(tt.dtdq0[0], r["dtdq0"]) < TOL and rel(tt.dtdelements[0], r["dtdelements"]) < TOL
+    assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+
+
 def test_errors_are_loud(nb, elements):
-    ic = nb.ElementsIC(0.0, 3, elements)
-    s = nb.State(ic)
-    s.pair[0, 1] = True
+    # fast-kick pairs are built for nbody <= 8 only: anything larger is refused, not silently ignored
+    n = 10
+    el = np.zeros((n, 7)); el[0, 0] = 1.0
+    for k in range(1, n):
+        el[k] = [3e-5, 1.5 * 1.6 ** (k - 1), 0.1 * k, 0.01, 0.0, np.pi / 2, 0.0]
+    s = nb.State(nb.ElementsIC(0.0, n, el))
+    s.pair[1, 2] = True
     with pytest.raises(nb.NbgError):
         nb.Integrator(0.05, 1.0)(s, 2)
     import ctypes as C
@@ -280,3 +327,30 @@ def test_small_event_chunks(nb, oracle, elements):
     nb.Integrator(0.05, 6.0)(a, ta)
     nb.Integrator(0.05, 6.0, stream_budget=1)(b, tb)
     assert np.array_equal(ta.tt, tb.tt) and np.array_equal(ta.dtdq0, tb.dtdq0) and np.array_equal(a.jac_step, b.jac_step)
+
+
+def test_full_size_batch_65536(nb, oracle, elements):
+    # BASELINE cfg 2 at its full batch size (65,536 perturbed TRAPPIST-1 systems, h = 0.06, grad) over a short window:
+    # (i) sampled systems against the oracle at 1e-11, (ii) batch independence: system 0 (unperturbed) is bit-identical to the
+    # same system run alone, (iii) every system detects the same number of transits as the unperturbed one +- 1 per body.
+    B, n, t0, h, tmax = 65536, 8, 7257.0, 0.06, 1.92
+    rng = np.random.Generator(np.random.Philox(key=20211582))
+    elb = np.broadcast_to(elements, (B, n, 7)).copy()
+    xi = rng.standard_normal((B, n - 1, 5)); xi[0] = 0.0
+    elb[:, 1:, 0] *= 1 + 1e-4 * xi[..., 0]; elb[:, 1:, 1] *= 1 + 1e-4 * xi[..., 1]
+    elb[:, 1:, 2] += 1e-4 * xi[..., 2]; elb[:, 1:, 3] += 1e-4 * xi[..., 3]; elb[:, 1:, 4] += 1e-4 * xi[..., 4]
+    ic = nb.ElementsIC(t0, n, elb)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s, tt)
+    assert not (s.status & ~np.uint32(2)).any()     # only the (reference-conform) Newton iteration cap may be flagged
+    for b in (0, 1, 31, 32, 4097, 65535):
+        so, r = _tt_oracle(oracle, elb[b], t0, h, tmax, tt.ntt)
+        _cmp_tt(tt.tt[b], tt.count[b], r)
+        assert rel(tt.dtdq0[b], r["dtdq0"]) < TOL and rel(tt.dtdelements[b], r["dtdelements"]) < TOL
+        assert rel(s.x[b], so["x"]) < TOL and rel(s.v[b], so["v"]) < TOL and rel(s.jac_step[b], so["jac_step_cm"].T) < TOL
+    ic1 = nb.ElementsIC(t0, n, elb[:1])
+    s1, tt1 = nb.State(ic1), nb.TransitTiming(tmax, ic1)
+    nb.Integrator(h, tmax)(s1, tt1)
+    assert np.array_equal(s1.x[0], s.x[0]) and np.array_equal(s1.jac_step[0], s.jac_step[0])
+    assert np.array_equal(tt1.tt[0], tt.tt[0]) and np.array_equal(tt1.dtdq0[0], tt.dtdq0[0])
+    assert np.all(np.abs(tt.count - tt.count[0]) <= 1)
