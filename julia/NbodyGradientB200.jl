@@ -72,7 +72,7 @@ function pack(ss::Vector{State{Float64}})
     B, n = length(ss), ss[1].n
     all(s -> s.n == n, ss) || throw(ArgumentError("all systems of a batch must have the same number of bodies"))
     all(s -> s.t[1] == ss[1].t[1], ss) || throw(ArgumentError("all systems of a batch must share s.t"))
-    any(s -> any(s.pair), ss) && throw(NbgError(Int32(-4), "s.pair must be all-false"))
+    all(s -> s.pair == ss[1].pair, ss) || throw(ArgumentError("all systems of a batch must share s.pair"))
     x = Array{Float64}(undef, 3, n, B); v = similar(x); xe = similar(x); ve = similar(x)
     m = Array{Float64}(undef, n, B)
     for (b, s) in enumerate(ss)
@@ -83,6 +83,8 @@ end
 
 function upload(p, ss::Vector{State{Float64}}, grad::Bool)
     x, v, m, xe, ve = pack(ss)
+    # s.pair: Matrix{Bool} is one byte per entry in column-major order, exactly what nbg_set_pair reads
+    chk(ccall((:nbg_set_pair, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), p, any(ss[1].pair) ? reinterpret(UInt8, ss[1].pair) : C_NULL))
     B, M = length(ss), 7 * ss[1].n
     if grad
         js = Array{Float64}(undef, M, M, B); je = similar(js); dq = Array{Float64}(undef, M, B)

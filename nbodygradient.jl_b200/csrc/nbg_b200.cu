@@ -64,7 +64,7 @@ struct TransitOut {
 // Launch bounds: the light (split-path) instantiation is capped at 128 registers so that 4 blocks fit an SM: a thread owns
 // a system for the whole chunk, so 65,536 systems must all be resident at once (148 SMs x 512 threads) or the kernel pays
 // a nearly empty second wave.
-template <bool GRAD, int EMIT>
+template <bool GRAD, int EMIT, bool KICKS = false>
 __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, double* scal, int detect, int ti,
                                                    double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
                                                    int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err, uint32_t kmask) {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel
   for (int s = 0; s < nsteps; ++s) {
     Emit em{EMIT ? stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys) : nullptr, TILE, (size_t)(sys % TILE),
             EMIT == 2 ? scal + tile_offset((size_t)2 * npairs(n) * SCF, ld / TILE, (size_t)s, (size_t)sys) : nullptr};
-    ahl21_step<GRAD, EMIT>(b, dq, n, h, em, kmask);
+    ahl21_step<GRAD, EMIT, KICKS>(b, dq, n, h, em, kmask);
     if (time_mode_kahan) ksum(tnow, terr, h);                      // (intr)(s,N): Integrator.jl:229
     else tnow = t0 + ((double)(istep0 + s + 1) * h);               // Transits.jl:161
     if (detect) {
@@ -157,7 +157,7 @@ __global__ void gsave_init_kernel(TrajArrays T, int n, long nsys, int ti) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // findtransit! (timing.jl:31-110).  One thread per queued transit.
-template <bool GRAD>
+template <bool GRAD, bool KICKS = false>
 __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(*Q.n, Q.cap);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
     tt2 = tt1;
     tt1 = dt0;
     b = b0;
-    ahl21_step<true, 0>(b, dq, n, dt0, none, kmask);
+    ahl21_step<true, 0, KICKS>(b, dq, n, dt0, none, kmask);
     const double gs = gsky(b, ti, j);
     const double gd = gdot(b, dq, ti, j);
     const double dt = -gs / gd;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   if (GRAD) {
     b = b0;
     Emit em{Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
-    ahl21_step<true, 1>(b, dq, n, dt0, em, kmask);
+    ahl21_step<true, 1, KICKS>(b, dq, n, dt0, em, kmask);
   }
   const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
   const double dvx = b.v[3 * j] - b.v[3 * ti], dvy = b.v[3 * j + 1] - b.v[3 * ti + 1];
@@ -606,6 +606,8 @@ struct nbg_plan {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // uploads that overlap the stepping (jac_init)
   cudaEvent_t copy_done = nullptr;
+  cudaStream_t aux_stream = nullptr;   // operator kernels of the main steps, concurrent with the transit refinement
+  cudaEvent_t ev_traj = nullptr, ev_ops = nullptr;
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
   DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
@@ -650,13 +652,15 @@ size_t jac_smem_bytes(int n, bool stage_phi) {
 struct Timer {
   cudaStream_t s;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
-  void begin(int kind) {
+  cudaStream_t cur = nullptr;
+  void begin(int kind, cudaStream_t on = nullptr) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, s);
+    cur = on ? on : s;
+    cudaEventRecord(a, cur);
     ev.push_back({kind, {a, b}});
   }
-  void end() { cudaEventRecord(ev.back().second.second, s); }
+  void end() { cudaEventRecord(ev.back().second.second, cur); }
   void collect(double* ms4) {
     for (auto& e : ev) {
       float t = 0;
@@ -764,41 +768,60 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
                                                          evmask ? evmask + o * ld : nullptr, kahan_time, tkerr, p->kmask);
         if (s_light > 0) p->launches++;
       }
+    } else if (grad && kicks) {
+      traj_kernel<true, 1, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
+                                                             p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
     } else if (grad) {
       traj_kernel<true, 1><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
                                                        p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+    } else if (kicks) {
+      traj_kernel<false, 0, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr,
+                                                              p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
     } else {
       traj_kernel<false, 0><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
                                                          Q, evlist, evmask, kahan_time, tkerr, p->kmask);
     }
     tm.end();
     p->launches++;
-    if (detect) {
-      tm.begin(1);
-      const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
-      if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
-      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
-      tm.end();
-      p->launches++;
+    // The operator kernels of the main steps (pair_op, phi_dense) depend only on the trajectory kernel; they run on the aux
+    // stream next to the transit refinement (latency-bound, few threads) and join before the Jacobian kernel.
+    const bool fork = grad && (s_split > 0 || use_rx);
+    if (fork) {
+      CK(cudaEventRecord(p->ev_traj, p->stream));
+      CK(cudaStreamWaitEvent(p->aux_stream, p->ev_traj, 0));
     }
     if (s_split > 0) {
-      tm.begin(6);
+      tm.begin(6, p->aux_stream);
       const int py = 4;
       const dim3 grid((unsigned)(ld / TILE), (unsigned)s_split, (unsigned)((2 * npairs(n) + py - 1) / py)), block(TILE, py);
-      pair_op_kernel<<<grid, block, 0, p->stream>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys);
+      pair_op_kernel<<<grid, block, 0, p->aux_stream>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys);
       tm.end();
       p->launches++;
     }
     if (grad && use_rx) {
-      tm.begin(5);
-      if (launch_phi_dense(p->stream, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      tm.begin(5, p->aux_stream);
+      if (launch_phi_dense(p->aux_stream, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      tm.end();
       p->launches++;
-      if (detect) {
+    }
+    if (fork) CK(cudaEventRecord(p->ev_ops, p->aux_stream));
+    if (detect) {
+      tm.begin(1);
+      const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
+      if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
+      else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
+      else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
+      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
+      tm.end();
+      p->launches++;
+      if (grad && use_rx) {
+        tm.begin(5);
         if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+        tm.end();
         p->launches++;
       }
-      tm.end();
     }
+    if (fork) CK(cudaStreamWaitEvent(p->stream, p->ev_ops, 0));
     if (grad) {
       p->counters_host[6] = (unsigned long long)S;
       p->counters_host[7] += 1;
@@ -895,6 +918,9 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&p->ev_traj, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&p->ev_ops, cudaEventDisableTiming));
   if (stream_budget_bytes <= 0) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
@@ -922,6 +948,8 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   cudaStreamDestroy(p->stream);
   cudaStreamDestroy(p->copy_stream);
   cudaEventDestroy(p->copy_done);
+  cudaStreamDestroy(p->aux_stream);
+  cudaEventDestroy(p->ev_traj); cudaEventDestroy(p->ev_ops);
   delete p;
   return NBG_OK;
 }
@@ -1030,7 +1058,9 @@ static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e
   float tot = 0;
   cudaEventElapsedTime(&tot, e0, e1);
   p->timings[4] = tot;
-  p->timings[3] = tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6];
+  // pair_op / phi_dense run on the aux stream concurrently with the transit kernel, so the per-kernel times can add up to more
+  // than the total; "other" is what is left of the total, never negative
+  p->timings[3] = std::max(0.0, tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6]);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);

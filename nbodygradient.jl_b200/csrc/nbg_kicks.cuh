@@ -210,8 +210,10 @@ __device__ __forceinline__ void phi_kicked_section(Body& b, double* dq, int n, d
 // dq: d(state)/dh, 6 entries per body (x then v); mass entries are identically zero and not stored.
 // em.base points at this step's region of the operator stream (used when EMIT).
 // kmask: bit p set = pair p (rx_pair_index order) is a fast-kick pair (s.pair[i,j]); 0 = the reference default.
-template <bool GRAD, int EMIT>
-__device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em, uint32_t kmask = 0u) {
+// KICKS = false compiles the fast-kick branches out (the default path pays nothing for them).
+template <bool GRAD, int EMIT, bool KICKS = false>
+__device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em, uint32_t kmask_in = 0u) {
+  const uint32_t kmask = KICKS ? kmask_in : 0u;
   const double h2 = 0.5 * h;
   const int P = npairs(n);
   // fill!(s.dqdt,0); kickfast!; drift_grad!/drift!; dqdt[x] = v/2 + h2 dqdt[v]   (ahl21.jl:8-21)
