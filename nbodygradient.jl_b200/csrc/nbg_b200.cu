@@ -155,10 +155,20 @@ __global__ void gsave_init_kernel(TrajArrays T, int n, long nsys, int ti) {
   }
 }
 
+// One gradient-free AHL21 step followed by the Newton correction -g / (dg/dt along the flow): kept out of line so that the
+// reference-form iterations of transit_kernel compile exactly as they do without it.
+template <bool KICKS>
+__device__ __noinline__ double transit_pre_iteration(const Body& b0, int n, double dt0, int ti, int j, uint32_t kmask) {
+  Body b = b0;
+  Emit none{nullptr, 0, 0};
+  ahl21_step<false, 0, KICKS>(b, nullptr, n, dt0, none, kmask);
+  return dt0 - gsky(b, ti, j) / gdot_flow(b, n, ti, j);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // findtransit! (timing.jl:31-110).  One thread per queued transit.
 template <bool GRAD, bool KICKS = false>
-__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask) {
+__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask, int npre) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(*Q.n, Q.cap);
   if (e >= nq) return;
@@ -174,9 +184,14 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   for (int q = 0; q < n; ++q) b0.m[q] = T.m[q * ld + sys];
   double dq[6 * NMAX];
   double dt0 = Q.dt0[e], stmp = 0.0;
+  Emit none{nullptr, 0, 0};
+  // Better starting guess for the reference's Newton iteration: `npre` gradient-free iterations (no pair Jacobians, no dq/dh;
+  // derivative of g along the exact flow).  The reference-form iterations below then start next to their fixed point and
+  // stop after one or two passes instead of three or four; the converged dt0 is the same fixed point.
+#pragma unroll 1
+  for (int pre = 0; pre < npre; ++pre) dt0 = transit_pre_iteration<KICKS>(b0, n, dt0, ti, j, kmask);
   double tt1 = dt0 + 1.0, tt2 = dt0 + 2.0;
   int iter = 0;
-  Emit none{nullptr, 0, 0};
   while (true) {
     tt2 = tt1;
     tt1 = dt0;
@@ -617,6 +632,7 @@ struct nbg_plan {
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
+  int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
@@ -808,10 +824,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     if (detect) {
       tm.begin(1);
       const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
-      if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
-      else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
-      else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
-      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask);
+      if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+      else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+      else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       tm.end();
       p->launches++;
       if (grad && use_rx) {
@@ -930,6 +946,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
+  if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
   if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   *out = p;

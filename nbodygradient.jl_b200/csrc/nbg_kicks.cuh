@@ -21,7 +21,7 @@ namespace nbg {
 constexpr int PF_KAPPA = 22;
 constexpr int PF_CLASS = 23;
 
-__device__ __forceinline__ bool kicked(uint32_t kmask, int p) { return (kmask >> p) & 1u; }
+__device__ __forceinline__ bool kicked(uint32_t kmask, int p) { return p < 32 && ((kmask >> p) & 1u); }
 
 // kickfast!(s,d,hk) over the flagged pairs.  first: the call at the start of the step (dq/dh is still zero there, ahl21.jl:9-14).
 template <bool GRAD, int EMIT>
@@ -274,5 +274,26 @@ __device__ __forceinline__ double gdot(const Body& b, const double* dq, int i, i
           (b.v[3 * j] - b.v[3 * i]) * (dq[6 * j] - dq[6 * i]) + (b.v[3 * j + 1] - b.v[3 * i + 1]) * (dq[6 * j + 1] - dq[6 * i + 1]));
 }
 
+
+// d g / d t along the exact flow, from the instantaneous Newtonian accelerations of bodies i and j: the derivative used by the
+// gradient-free pre-iterations of the transit Newton solve (transit_kernel).  The reference's own derivative (gd!, timing.jl:147-150:
+// the step-size derivative of the AHL21 MAP) differs from it by the integrator's truncation error only.
+__device__ __forceinline__ double gdot_flow(const Body& b, int n, int i, int j) {
+  double a[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const int who[2] = {i, j};
+#pragma unroll
+  for (int w = 0; w < 2; ++w)
+    for (int l = 0; l < n; ++l) {
+      if (l == who[w]) continue;
+      const double r0 = b.x[3 * who[w]] - b.x[3 * l], r1 = b.x[3 * who[w] + 1] - b.x[3 * l + 1], r2 = b.x[3 * who[w] + 2] - b.x[3 * l + 2];
+      const double d2 = r0 * r0 + r1 * r1 + r2 * r2;
+      const double f = kG * b.m[l] / (d2 * sqrt(d2));
+      a[w][0] -= f * r0;
+      a[w][1] -= f * r1;
+    }
+  const double dx = b.x[3 * j] - b.x[3 * i], dy = b.x[3 * j + 1] - b.x[3 * i + 1];
+  const double dvx = b.v[3 * j] - b.v[3 * i], dvy = b.v[3 * j + 1] - b.v[3 * i + 1];
+  return dvx * dvx + dvy * dvy + dx * (a[1][0] - a[0][0]) + dy * (a[1][1] - a[0][1]);
+}
 
 }  // namespace nbg
