@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--ref-systems-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-input", choices=["elements", "cartesian"], default="cartesian",
+                    help="what crosses PCIe on the way in: orbital elements (init_nbody on the device) or x, v, m + host-computed jac_init")
     ap.add_argument("--e2e-slices", type=int, default=1, help="slices (plans + host threads) of the end-to-end arm")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -258,16 +260,23 @@ def main():
             pl = C.c_void_p()
             _lib.check(L.nbg_plan_create(C.byref(pl), C.c_int32(NBODY), C.c_int64(ns), C.c_int32(local), C.c_int64(int(free_b // (5 * K)))))
             bufs = dict(x=pin(x[lo:hi])[1], v=pin(v[lo:hi])[1], m=pin(m[lo:hi])[1], j=pin(jac_init[lo:hi].transpose(0, 2, 1))[1],
+                        el=pin(elb[lo:hi].transpose(0, 2, 1))[1],
                         tt=pin(np.zeros((ns, RT)))[1], c=pin(np.zeros((ns, NBODY), dtype=np.int64))[1], d=pin(np.zeros((ns, RT, M)))[1],
                         e=pin(np.zeros((ns, RT, M)))[1], xo=pin(np.zeros((ns, NBODY, 3)))[1], vo=pin(np.zeros((ns, NBODY, 3)))[1])
-            h2d += sum(bufs[k].nbytes for k in ("x", "v", "m", "j"))
+            h2d += sum(bufs[k].nbytes for k in (("x", "v", "m", "j") if args.e2e_input == "cartesian" else ("el",)))
             d2h += sum(bufs[k].nbytes for k in ("tt", "c", "d", "e", "xo", "vo"))
             slices.append((pl, bufs))
 
         def step_e2e(pl, B):
-            _lib.check(L.nbg_transit_timing(pl, ptr(B["x"]), ptr(B["v"]), ptr(B["m"]), None, C.c_double(T0), C.c_double(H), C.c_double(tmaxw),
-                                            C.c_int32(0), ptr(ntt), C.c_int32(0), C.c_int32(1), ptr(B["j"]), ptr(B["tt"]), ptr(B["c"]), ptr(B["d"]),
-                                            ptr(B["e"]), ptr(B["xo"]), ptr(B["vo"]), None, None, None, None, None, None, None))
+            if args.e2e_input == "cartesian":   # x, v, m and the host-computed jac_init go up (1.6 GB of jac_init)
+                _lib.check(L.nbg_transit_timing(pl, ptr(B["x"]), ptr(B["v"]), ptr(B["m"]), None, C.c_double(T0), C.c_double(H), C.c_double(tmaxw),
+                                                C.c_int32(0), ptr(ntt), C.c_int32(0), C.c_int32(1), ptr(B["j"]), ptr(B["tt"]), ptr(B["c"]), ptr(B["d"]),
+                                                ptr(B["e"]), ptr(B["xo"]), ptr(B["vo"]), None, None, None, None, None, None, None))
+            else:   # the reference's user-level sequence ElementsIC -> State -> intr(s, tt): orbital elements go up, init_nbody runs on the device
+                _lib.check(L.nbg_set_state_elements(pl, ptr(B["el"]), None, C.c_double(T0), C.c_int32(1)))
+                _lib.check(L.nbg_transit_timing_resident(pl, C.c_double(H), C.c_double(tmaxw), C.c_int32(0), ptr(ntt), C.c_int32(0), C.c_int32(1), None))
+                _lib.check(L.nbg_transit_fetch(pl, ptr(B["tt"]), ptr(B["c"]), ptr(B["d"]), ptr(B["e"])))
+                _lib.check(L.nbg_get_state(pl, ptr(B["xo"]), ptr(B["vo"]), None, None, None, None, None, None, None))
 
         gate = threading.Barrier(K + 1)
         errs = []
@@ -299,7 +308,7 @@ def main():
         if dist is not None:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * main_steps / (float(t2.item()) * 1e-3), "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "slices": K, "transits_checked": int(sum(B["c"].sum() for _, B in slices)),
+               "d2h_bytes_per_step": int(d2h), "slices": K, "input": args.e2e_input, "transits_checked": int(sum(B["c"].sum() for _, B in slices)),
                "timing": "host wall clock around %d blocking nbg_transit_timing calls per slice, max over ranks" % args.steps}
         for pl, _B in slices:
             L.nbg_plan_destroy(pl)

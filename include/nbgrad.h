@@ -74,6 +74,15 @@ int32_t nbg_set_state(nbg_plan* plan, const double* x, const double* v, const do
 int32_t nbg_get_state(nbg_plan* plan, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error,
                       double* dqdt, double* t, uint32_t* status);
 
+/* State(ic::ElementsIC) computed on the device (init_nbody, src/ics/init_nbody.jl:13-27; kepler_init, src/ics/kepler_init.jl:66-210):
+ * elements[sys][c][i] is Julia's elements[i,c] (n x 7 column-major: m, P, t0, ecosw, esinw, I, Omega) with the system index slowest;
+ * eps is the n x n hierarchy matrix ic.epsilon (Julia column-major, one for the whole batch) or NULL = fully nested
+ * (ElementsIC(t0, N::Int, elements)).  Sets x, v, m and the State(ic) defaults, and -- if want_jac_init -- keeps
+ * jac_init = d(x,v,m)/d(elements,m) resident: nbg_transit_timing_resident with jac_init == NULL then uses it for dtdelements.
+ * nbg_get_jac_init downloads it ([sys][col][row]). */
+int32_t nbg_set_state_elements(nbg_plan* plan, const double* elements, const double* eps, double t0, int32_t want_jac_init);
+int32_t nbg_get_jac_init(nbg_plan* plan, double* jac_init);
+
 /* ---- plain integration on the resident state -----------------------------------------------------------------
  * nsteps steps of size h, then (if h_last != 0) one step of size h_last — exactly what (intr)(s,time) does with
  * nsteps = |round((time-t0)/h)| and h_last = time - (t0 + h*nsteps) (Integrator.jl:159-197).
@@ -95,7 +104,8 @@ int32_t nbg_integrate(nbg_plan* plan, const double* x0, const double* v0, const 
  *   dtdq0[sys][off[i]+k][7*p+q]   d tt / d (q-th coordinate of body p)   (Julia tt.dtdq0[i,k,q,p])
  *   dtdelements[...] same shape    dtdq0 . jac_init                       (Julia tt.dtdelements[i,k,l,k'])
  * With ntt_body[i] = ntt for all i this is the reference's dense TransitTiming with a permuted index order; unfilled
- * slots are 0 (Transits.jl:46-48).  jac_init is [sys][col][row] (Julia column-major), NULL = skip dtdelements.
+ * slots are 0 (Transits.jl:46-48).  jac_init is [sys][col][row] (Julia column-major); NULL = use the device-computed one of
+ * nbg_set_state_elements if there is one, else skip dtdelements.
  * mode 0 = TransitTiming; mode 1 = TransitParameters: tt/dtdq0/dtdelements get a leading component axis of 3
  * (time, v_sky, b_sky^2): ttbv[sys][off[i]+k][3], dtbvdq0[sys][off[i]+k][7*p+q][3].
  * grad = 0: times only (dtdq0/dtdelements untouched, no Jacobian propagated).

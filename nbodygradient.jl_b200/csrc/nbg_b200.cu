@@ -22,6 +22,7 @@
 
 #include "../../include/nbgrad.h"
 #include "nbg_jacobian_rx.cuh"
+#include "nbg_ics.cuh"
 
 using namespace nbg;
 
@@ -627,7 +628,7 @@ struct nbg_plan {
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
   DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
-  DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters;
+  DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters, belem;
   DevBuf stage[8];  // staging for host<->device conversions
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
@@ -636,6 +637,7 @@ struct nbg_plan {
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
+  bool jinit_resident = false;  // bjinit holds jac_init computed on the device by nbg_set_state_elements
   unsigned long long counters_host[8] = {0};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
@@ -959,7 +961,7 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   cudaStreamSynchronize(p->stream);
   DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
                    &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
-                   &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters};
+                   &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters, &p->belem};
   for (auto* b : all) b->release();
   for (auto& b : p->stage) b.release();
   cudaStreamDestroy(p->stream);
@@ -1019,6 +1021,78 @@ int32_t nbg_set_state(nbg_plan* p, const double* x, const double* v, const doubl
   CK(cudaStreamSynchronize(p->stream));
   p->has_state = true;
   p->have_transit = false;
+  p->jinit_resident = false;
+  return NBG_OK;
+}
+
+// State(ic::ElementsIC) on the device: init_nbody (src/ics/init_nbody.jl:13-27) for every system of the batch.
+int32_t nbg_set_state_elements(nbg_plan* p, const double* elements, const double* eps, double t0, int32_t want_jac_init) {
+  if (!p || !elements) return fail(NBG_ERR_ARG, "plan and elements are required");
+  CK(cudaSetDevice(p->device));
+  const size_t n = p->n, nsys = p->nsys, M = 7 * n;
+  IcsHierarchy H;
+  std::memset(&H, 0, sizeof(H));
+  if (eps) {
+    for (size_t q = 0; q < n * n; ++q) H.eps[q] = eps[q];
+  } else {  // fully nested: ElementsIC(t0, N::Int, elements) -> hierarchy([N, ones(N-1)...])  (setup_hierarchy.jl:9-29)
+    for (size_t i = 0; i + 1 < n; ++i) {
+      for (size_t j = 0; j <= i; ++j) H.eps[i + n * j] = -1.0;
+      H.eps[i + n * (i + 1)] = 1.0;
+    }
+    for (size_t j = 0; j < n; ++j) H.eps[(n - 1) + n * j] = -1.0;
+  }
+  {  // elements row of each Keplerian: the i+1+b bookkeeping of kepcalc (init_nbody.jl:66-103), a function of eps alone
+    int i = 1, b = 0;
+    while (i < (int)n) {
+      if (H.eps[(i - 1) + 0] == 0.0) b += 1;
+      const int row = i + b;
+      if (row < 0 || row >= (int)n) return fail(NBG_ERR_ARG, "hierarchy matrix does not map Keplerians to element rows");
+      H.row[i - 1] = row;
+      if (b > 0) b -= 2; else if (b < 0) b = 0;
+      i += 1;
+    }
+  }
+  CK(cudaStreamSynchronize(p->copy_stream));  // a previous jac_init kernel may still read the elements buffer
+  if (p->belem.ensure(7 * n * nsys * 8)) return fail(NBG_ERR_NOMEM, "elements allocation failed");
+  CK(cudaMemcpyAsync(p->belem.p, elements, 7 * n * nsys * 8, cudaMemcpyHostToDevice, p->stream));
+  if (want_jac_init && p->bjinit.ensure(nsys * M * M * 8)) return fail(NBG_ERR_NOMEM, "jac_init allocation failed");
+  // errors, dq/dh, status, time: the State(ic) defaults (Integrator.jl:82-103)
+  CK(cudaMemsetAsync(p->bxe.p, 0, 3 * n * p->ld * 8, p->stream));
+  CK(cudaMemsetAsync(p->bve.p, 0, 3 * n * p->ld * 8, p->stream));
+  CK(cudaMemsetAsync(p->bdq.p, 0, 6 * n * p->ld * 8, p->stream));
+  CK(cudaMemsetAsync(p->bstatus.p, 0, p->ld * 4, p->stream));
+  CK(cudaMemsetAsync(p->bterr.p, 0, p->ld * 8, p->stream));
+  std::vector<double> tv(p->ld, t0);
+  CK(cudaMemcpyAsync(p->bt.p, tv.data(), p->ld * 8, cudaMemcpyHostToDevice, p->stream));
+  const int tpb = 64;
+  // x, v, m now; jac_init (only needed by the dtdelements kernel at the end of a transit-timing call) on the copy stream, so that
+  // it overlaps the stepping -- nbg_transit_timing_resident / nbg_get_jac_init wait for copy_done
+  ics_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->belem.as<double>(), H, (int)n, (long)nsys, p->ld, t0, p->T.x, p->T.v, p->T.m,
+                                                                         nullptr, 1);
+  p->launches++;
+  CK(cudaStreamSynchronize(p->stream));
+  if (want_jac_init) {
+    ics_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->copy_stream>>>(p->belem.as<double>(), H, (int)n, (long)nsys, p->ld, t0, p->T.x, p->T.v,
+                                                                                p->T.m, p->bjinit.as<double>(), 0);
+    p->launches++;
+    CK(cudaEventRecord(p->copy_done, p->copy_stream));
+  }
+  CK(cudaGetLastError());
+  p->jac_valid = false;
+  p->has_state = true;
+  p->have_transit = false;
+  p->jinit_resident = want_jac_init != 0;
+  return NBG_OK;
+}
+
+int32_t nbg_get_jac_init(nbg_plan* p, double* jac_init) {
+  if (!p || !jac_init) return fail(NBG_ERR_ARG, "NULL argument");
+  if (!p->jinit_resident) return fail(NBG_ERR_ARG, "no device-computed jac_init (call nbg_set_state_elements with want_jac_init)");
+  CK(cudaSetDevice(p->device));
+  const size_t M = 7 * (size_t)p->n;
+  CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
+  CK(cudaMemcpyAsync(jac_init, p->bjinit.p, p->nsys * M * M * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
   return NBG_OK;
 }
 
@@ -1160,11 +1234,14 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   gsave_init_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T, n, (long)nsys, ti);
   p->launches++;
   // jac_init (M^2 doubles per system, the bulk of the input bytes) is uploaded on a second stream while the steps run
-  const bool want_dtde = grad && jac_init;
+  const bool want_dtde = grad && (jac_init || p->jinit_resident);
   if (want_dtde) {
-    if (p->bjinit.ensure(nsys * M * M * 8) || p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
+    if ((jac_init && p->bjinit.ensure(nsys * M * M * 8)) || p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
       return fail(NBG_ERR_NOMEM, "dtdelements allocation failed");
-    CK(cudaMemcpyAsync(p->bjinit.p, jac_init, nsys * M * M * 8, cudaMemcpyHostToDevice, p->copy_stream));
+    if (jac_init) {
+      CK(cudaMemcpyAsync(p->bjinit.p, jac_init, nsys * M * M * 8, cudaMemcpyHostToDevice, p->copy_stream));
+      p->jinit_resident = false;
+    }  // else: the ics_kernel launched by nbg_set_state_elements on the copy stream produces it
     CK(cudaMemsetAsync(p->bdtde.p, 0, nsys * RT * M * C * 8, p->copy_stream));
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
   }

@@ -10,7 +10,7 @@ ERRORS = {-1: "NBG_ERR_ARG", -2: "NBG_ERR_NO_DEVICE", -3: "NBG_ERR_CUDA", -4: "N
 ST_NONFINITE, ST_TRANSIT_ITMAX, ST_EVENT_OVERFLOW, ST_NTT_OVERFLOW = 1, 2, 4, 8
 
 # every symbol include/nbgrad.h declares
-SYMBOLS = ["nbg_version", "nbg_last_error", "nbg_device_count", "nbg_plan_create", "nbg_plan_destroy", "nbg_set_pair", "nbg_set_state", "nbg_get_state",
+SYMBOLS = ["nbg_version", "nbg_last_error", "nbg_device_count", "nbg_plan_create", "nbg_plan_destroy", "nbg_set_pair", "nbg_set_state", "nbg_set_state_elements", "nbg_get_jac_init", "nbg_get_state",
            "nbg_integrate_resident", "nbg_integrate", "nbg_transit_timing_resident", "nbg_transit_fetch", "nbg_transit_timing",
            "nbg_counters", "nbg_counters_reset", "nbg_last_timings", "nbg_cuda_stream", "nbg_fp64_peak"]
 

@@ -57,8 +57,16 @@ def check_step(t0, tmax):
 class State:
     """State(ic) — Integrator.jl:82-103."""
 
-    def __init__(self, ic):
-        x, v, jac_init = ic.init_nbody()
+    def __init__(self, ic, on_device=False, device=0):
+        """on_device=True: init_nbody (elements -> x, v, jac_init) runs in libnbgrad_b200 (nbg_set_state_elements) instead of
+        the numpy IC layer; the state stays resident, so the next Integrator call skips the upload of x, v, m and jac_init."""
+        self._resident_plan = None
+        if on_device:
+            if not hasattr(ic, "elements"):
+                raise TypeError("State(ic, on_device=True) needs an ElementsIC")
+            x, v, jac_init = self._init_on_device(ic, device)
+        else:
+            x, v, jac_init = ic.init_nbody()
         B, n = x.shape[0], ic.nbody
         M = 7 * n
         self.n = n
@@ -76,9 +84,31 @@ class State:
         self.pair = np.zeros((n, n), dtype=bool)
         self.status = np.zeros(B, dtype=np.uint32)
 
+    def _init_on_device(self, ic, device):
+        L = _lib.lib()
+        B, n = ic.elements.shape[0], ic.nbody
+        M = 7 * n
+        plan = _plan(n, B, device, 0)
+        el = ic.elements.copy()
+        el[:, :, 0] = ic.m                                               # masses live in ic.m (as in ic.init_nbody)
+        el = np.ascontiguousarray(el.transpose(0, 2, 1))                # [sys][c][i] = Julia elements[i,c], system slowest
+        eps = np.asfortranarray(np.asarray(ic.eps, dtype=np.float64))   # Julia column-major n x n
+        check(L.nbg_set_state_elements(plan, ptr(el), ptr(eps), C.c_double(float(ic.t0)), C.c_int32(1 if ic.der else 0)))
+        x, v = np.empty((B, n, 3)), np.empty((B, n, 3))
+        check(L.nbg_get_state(plan, ptr(x), ptr(v), None, None, None, None, None, None, None))
+        jac_init = None
+        if ic.der:
+            jcm = np.empty((B, M, M))
+            check(L.nbg_get_jac_init(plan, ptr(jcm)))
+            jac_init = jcm.transpose(0, 2, 1).copy()
+        self._resident_plan = plan   # the device already holds this state: the first Integrator call on it skips the upload
+        self._resident_sig = (float(x.sum()), float(v.sum()), float(ic.m.sum()))
+        return x, v, jac_init
+
     def copy(self):
         import copy
         s = copy.copy(self)
+        s._resident_plan = None
         for k, val in self.__dict__.items():
             if isinstance(val, np.ndarray) and k != "m":
                 setattr(s, k, val.copy())
@@ -90,7 +120,17 @@ class State:
 
     # -- device transfer helpers
     def _upload(self, plan, with_jac):
+        """Returns True if the state (and jac_init) was already resident from State(ic, on_device=True)."""
         L = _lib.lib()
+        if self._resident_plan is not None:
+            # still the state the device computed?  (the arrays are public: a caller may have edited them, e.g. tilt)
+            fresh = (self._resident_plan.value == plan.value and not self.jac_error.any() and not self.xerror.any() and
+                     self._resident_sig == (float(self.x.sum()), float(self.v.sum()), float(np.asarray(self.m).sum())))
+            self._resident_plan = None
+            if fresh:
+                pr = np.asfortranarray(self.pair.astype(np.uint8))
+                check(L.nbg_set_pair(plan, ptr(pr) if pr.any() else None))
+                return True
         pr = np.asfortranarray(self.pair.astype(np.uint8))  # Julia layout: [i,j] at i + n*j
         check(L.nbg_set_pair(plan, ptr(pr) if pr.any() else None))
         self._m_c = np.ascontiguousarray(self.m, dtype=np.float64)
@@ -98,6 +138,7 @@ class State:
         je = np.ascontiguousarray(self.jac_error.transpose(0, 2, 1)) if with_jac else None
         check(L.nbg_set_state(plan, ptr(self.x), ptr(self.v), ptr(self._m_c), C.c_double(float(self.t[0])), ptr(self.xerror), ptr(self.verror),
                               ptr(js), ptr(je), ptr(self.dqdt) if with_jac else None))
+        return False
 
     def _download(self, plan, with_jac):
         L = _lib.lib()
@@ -226,11 +267,12 @@ class Integrator:
         L = _lib.lib()
         plan = self._p(s)
         n, B, ntt, M = s.n, s.nsys, tt.ntt, 7 * s.n
-        s._upload(plan, grad)
+        resident = s._upload(plan, grad)
         ntt_body = np.full(n, ntt, dtype=np.int32)
         mode = 1 if tt.ncomp == 3 else 0
         ji = None
-        if grad and s.jac_init.size:
+        want_dtde = grad and s.jac_init.size
+        if want_dtde and not resident:   # resident: jac_init computed on the device is used (jac_init = NULL)
             ji = np.ascontiguousarray(s.jac_init.transpose(0, 2, 1))
         check(L.nbg_transit_timing_resident(plan, C.c_double(self.h), C.c_double(self.tmax), C.c_int32(tt.ti), ptr(ntt_body), C.c_int32(mode),
                                             C.c_int32(1 if grad else 0), ptr(ji)))
@@ -239,7 +281,7 @@ class Integrator:
         shp_d = (B, n, ntt, n, 7) if Cn == 1 else (B, n, ntt, n, 7, 3)
         t_raw = np.zeros(shp_t)
         d_raw = np.zeros(shp_d) if grad else None
-        e_raw = np.zeros(shp_d) if (grad and ji is not None) else None
+        e_raw = np.zeros(shp_d) if want_dtde else None
         check(L.nbg_transit_fetch(plan, ptr(t_raw), ptr(tt.count), ptr(d_raw), ptr(e_raw)))
         s._download(plan, grad)
         if Cn == 1:

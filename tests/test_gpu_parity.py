@@ -354,3 +354,39 @@ def test_full_size_batch_65536(nb, oracle, elements):
     assert np.array_equal(s1.x[0], s.x[0]) and np.array_equal(s1.jac_step[0], s.jac_step[0])
     assert np.array_equal(tt1.tt[0], tt.tt[0]) and np.array_equal(tt1.dtdq0[0], tt.dtdq0[0])
     assert np.all(np.abs(tt.count - tt.count[0]) <= 1)
+
+
+@pytest.mark.parametrize("n", [3, 8])
+def test_device_ic_layer(nb, oracle, elements, n):
+    # init_nbody / kepler_init on the device (nbg_set_state_elements) against the oracle's IC layer, and the
+    # transit-timing call that uses the resident state and the device-computed jac_init for dtdelements.
+    rng = np.random.default_rng(5)
+    B, t0, h, tmax = 4, 7257.0, 0.05, 8.0
+    elb = np.broadcast_to(elements[:n], (B, n, 7)).copy()
+    elb[1:, 1:, 0] *= 1 + 1e-3 * rng.standard_normal((B - 1, n - 1))
+    elb[1:, 1:, 3:5] += 1e-3 * rng.standard_normal((B - 1, n - 1, 2))
+    elb[2, 1:, 5] += 0.01 * rng.standard_normal(n - 1)      # inclinations off 90 degrees
+    elb[3, 1:, 6] += 0.01 * rng.standard_normal(n - 1)      # and nodes off zero
+    ic = nb.ElementsIC(t0, n, elb)
+    s = nb.State(ic, on_device=True)
+    for b in range(B):
+        x, v, jac = oracle.init_nbody(elb[b], t0)
+        assert rel(s.x[b], x) < TOL and rel(s.v[b], v) < TOL
+        assert rel(s.jac_init[b], jac) < TOL
+    tt = nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s, tt)                             # resident state + resident jac_init
+    s2, tt2 = nb.State(ic), nb.TransitTiming(tmax, ic)        # host IC layer, everything uploaded
+    nb.Integrator(h, tmax)(s2, tt2)
+    assert tt.count.sum() > 10 and np.array_equal(tt.count, tt2.count)
+    assert rel(tt.tt, tt2.tt) < TOL and rel(tt.dtdq0, tt2.dtdq0) < 1e-10 and rel(tt.dtdelements, tt2.dtdelements) < 1e-10
+    for b in range(B):
+        so, r = _tt_oracle(oracle, elb[b], t0, h, tmax, tt.ntt)
+        _cmp_tt(tt.tt[b], tt.count[b], r)
+        assert rel(tt.dtdelements[b], r["dtdelements"]) < TOL
+
+
+def test_device_ic_layer_circular_orbit(nb, oracle, elements):
+    el = elements[:3].copy(); el[1, 3:5] = 0.0               # ecc == 0 branch of kepler_init (kepler_init.jl:84-86, :197-200)
+    s = nb.State(nb.ElementsIC(7257.0, 3, el), on_device=True)
+    x, v, jac = oracle.init_nbody(el, 7257.0)
+    assert rel(s.x[0], x) < TOL and rel(s.v[0], v) < TOL and rel(s.jac_init[0], jac) < TOL
