@@ -390,3 +390,26 @@ def test_device_ic_layer_circular_orbit(nb, oracle, elements):
     s = nb.State(nb.ElementsIC(7257.0, 3, el), on_device=True)
     x, v, jac = oracle.init_nbody(el, 7257.0)
     assert rel(s.x[0], x) < TOL and rel(s.v[0], v) < TOL and rel(s.jac_init[0], jac) < TOL
+
+
+def test_cfg2_full_length_1600_days(nb, elements):
+    # BASELINE cfg 2 at its full LENGTH: TRAPPIST-1, h = 0.06 d over 1600 d = 26,667 steps, grad, ntt = 1062 (Transits.jl:44-45).
+    # All ~2,770 transit times and the final x, v at the north_star tolerance 1e-11.  Jacobian-type outputs (dtdq0, dtdelements,
+    # jac_step) accumulate round-off over 26,667 steps: two compilations of the oracle itself (with / without FMA contraction)
+    # differ by 1.0e-10 in max-norm there (profiles/r01_oracle_noise_floor.txt, tools/oracle_noise_floor.py), so that measured
+    # floor is the tolerance for them at this length; every shorter test keeps 1e-11.
+    from oracle.binding import Oracle
+    fast = Oracle(fast=True)   # -O3 + FMA build of the same restatement (half the run time of the -O2 build)
+    FLOOR = 1.0e-10
+    n, t0, h, tmax = 8, 7257.0, 0.06, 1600.0
+    ic = nb.ElementsIC(t0, n, elements)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    assert tt.ntt == 1062
+    nb.Integrator(h, tmax)(s, tt)
+    so, r = _tt_oracle(fast, elements, t0, h, tmax, tt.ntt)
+    assert 2700 < r["count"].sum() < 2800
+    _cmp_tt(tt.tt[0], tt.count[0], r)
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+    assert abs(s.t[0] - so["t"][0]) < 1e-9
+    assert rel(tt.dtdq0[0], r["dtdq0"]) < FLOOR and rel(tt.dtdelements[0], r["dtdelements"]) < FLOOR
+    assert rel(s.jac_step[0], so["jac_step_cm"].T) < FLOOR
