@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-input", choices=["elements", "cartesian"], default="cartesian",
                     help="what crosses PCIe on the way in: orbital elements (init_nbody on the device) or x, v, m + host-computed jac_init")
+    ap.add_argument("--e2e-output", choices=["arrays", "chi2"], default="arrays",
+                    help="with --e2e-input elements: copy out tt/dtdq0/dtdelements, or only the fused chi^2 and its gradients")
     ap.add_argument("--e2e-slices", type=int, default=1, help="slices (plans + host threads) of the end-to-end arm")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -260,11 +262,13 @@ def main():
             pl = C.c_void_p()
             _lib.check(L.nbg_plan_create(C.byref(pl), C.c_int32(NBODY), C.c_int64(ns), C.c_int32(local), C.c_int64(int(free_b // (5 * K)))))
             bufs = dict(x=pin(x[lo:hi])[1], v=pin(v[lo:hi])[1], m=pin(m[lo:hi])[1], j=pin(jac_init[lo:hi].transpose(0, 2, 1))[1],
-                        el=pin(elb[lo:hi].transpose(0, 2, 1))[1],
+                        el=pin(elb[lo:hi].transpose(0, 2, 1))[1], tobs=pin(np.full(RT, T0 + 1.0))[1], sig=pin(np.full(RT, 1e-3))[1],
+                        chi2=pin(np.zeros(ns))[1], gq=pin(np.zeros((ns, M)))[1], ge=pin(np.zeros((ns, M)))[1],
                         tt=pin(np.zeros((ns, RT)))[1], c=pin(np.zeros((ns, NBODY), dtype=np.int64))[1], d=pin(np.zeros((ns, RT, M)))[1],
                         e=pin(np.zeros((ns, RT, M)))[1], xo=pin(np.zeros((ns, NBODY, 3)))[1], vo=pin(np.zeros((ns, NBODY, 3)))[1])
             h2d += sum(bufs[k].nbytes for k in (("x", "v", "m", "j") if args.e2e_input == "cartesian" else ("el",)))
-            d2h += sum(bufs[k].nbytes for k in ("tt", "c", "d", "e", "xo", "vo"))
+            d2h += sum(bufs[k].nbytes for k in (("chi2", "gq", "ge") if (args.e2e_output == "chi2" and args.e2e_input == "elements")
+                                                else ("tt", "c", "d", "e", "xo", "vo")))
             slices.append((pl, bufs))
 
         def step_e2e(pl, B):
@@ -275,8 +279,11 @@ def main():
             else:   # the reference's user-level sequence ElementsIC -> State -> intr(s, tt): orbital elements go up, init_nbody runs on the device
                 _lib.check(L.nbg_set_state_elements(pl, ptr(B["el"]), None, C.c_double(T0), C.c_int32(1)))
                 _lib.check(L.nbg_transit_timing_resident(pl, C.c_double(H), C.c_double(tmaxw), C.c_int32(0), ptr(ntt), C.c_int32(0), C.c_int32(1), None))
-                _lib.check(L.nbg_transit_fetch(pl, ptr(B["tt"]), ptr(B["c"]), ptr(B["d"]), ptr(B["e"])))
-                _lib.check(L.nbg_get_state(pl, ptr(B["xo"]), ptr(B["vo"]), None, None, None, None, None, None, None))
+                if args.e2e_output == "chi2":   # fused likelihood: chi^2 + gradients (1 + 2M doubles per system) instead of the arrays
+                    _lib.check(L.nbg_transit_chi2(pl, ptr(B["tobs"]), ptr(B["sig"]), C.c_int32(0), ptr(B["chi2"]), ptr(B["gq"]), ptr(B["ge"])))
+                else:
+                    _lib.check(L.nbg_transit_fetch(pl, ptr(B["tt"]), ptr(B["c"]), ptr(B["d"]), ptr(B["e"])))
+                    _lib.check(L.nbg_get_state(pl, ptr(B["xo"]), ptr(B["vo"]), None, None, None, None, None, None, None))
 
         gate = threading.Barrier(K + 1)
         errs = []
@@ -308,7 +315,7 @@ def main():
         if dist is not None:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * main_steps / (float(t2.item()) * 1e-3), "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "slices": K, "input": args.e2e_input, "transits_checked": int(sum(B["c"].sum() for _, B in slices)),
+               "d2h_bytes_per_step": int(d2h), "slices": K, "input": args.e2e_input, "output": args.e2e_output if args.e2e_input == "elements" else "arrays", "transits_checked": int(sum(B["c"].sum() for _, B in slices)), "chi2_sum": float(sum(B["chi2"].sum() for _, B in slices)),
                "timing": "host wall clock around %d blocking nbg_transit_timing calls per slice, max over ranks" % args.steps}
         for pl, _B in slices:
             L.nbg_plan_destroy(pl)

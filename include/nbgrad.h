@@ -114,6 +114,14 @@ int32_t nbg_integrate(nbg_plan* plan, const double* x0, const double* v0, const 
 int32_t nbg_transit_timing_resident(nbg_plan* plan, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode,
                                     int32_t grad, const double* jac_init_host_or_null);
 int32_t nbg_transit_fetch(nbg_plan* plan, double* tt, int64_t* count, double* dtdq0, double* dtdelements);
+/* Fused transit-time likelihood on the results of the last nbg_transit_timing_resident call (mode 0): what an optimiser / HMC
+ * caller computes from tt, dtdq0, dtdelements (docs/src/gradients.md), reduced on the device so that 1 + 2M doubles per system are
+ * copied out instead of the full arrays:
+ *   chi2[sys] = sum ((tt - t_obs) / sigma)^2,   grad_q0[sys][7p+q] = sum 2 (tt - t_obs) / sigma^2 * dtdq0[..][7p+q],   grad_elements likewise
+ * over the stored transits.  t_obs, sigma use tt's slot layout ([off[i]+k]); per_system = 0: one table [RT] for the whole batch,
+ * 1: [sys][RT].  Slots with sigma <= 0 or a non-finite t_obs are skipped.  grad_q0 / grad_elements may be NULL. */
+int32_t nbg_transit_chi2(nbg_plan* plan, const double* t_obs, const double* sigma, int32_t per_system, double* chi2, double* grad_q0,
+                         double* grad_elements);
 int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0,
                            double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad,
                            const double* jac_init, double* tt, int64_t* count, double* dtdq0, double* dtdelements, double* x,

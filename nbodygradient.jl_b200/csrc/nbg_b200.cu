@@ -524,6 +524,42 @@ __global__ void dtdelements_kernel(const double* __restrict__ dtdq0, const doubl
   }
 }
 
+// Fused transit-time likelihood: chi^2 = sum ((tt - t_obs) / sigma)^2 over the stored transits of one system and
+// its gradients with respect to the initial Cartesian coordinates (dtdq0) and to the orbital elements (dtdelements), reduced on
+// the device: 1 + 2M doubles per system leave the GPU instead of the full dtdq0 / dtdelements arrays.  One block per system, one
+// thread per column; observations with sigma <= 0 (or a non-finite t_obs) are skipped.
+__global__ void chi2_kernel(const double* __restrict__ tt, const double* __restrict__ dtdq0, const double* __restrict__ dtde,
+                            const int32_t* __restrict__ count, const int32_t* __restrict__ ntt_body, const int32_t* __restrict__ off, int n, size_t ld,
+                            int RT, const double* __restrict__ tobs, const double* __restrict__ sigma, int per_system, double* __restrict__ chi2,
+                            double* __restrict__ gq, double* __restrict__ ge) {
+  const int M = 7 * n, c = threadIdx.x;
+  const long sys = blockIdx.x;
+  const double* to = tobs + (per_system ? (size_t)sys * RT : 0);
+  const double* sg = sigma + (per_system ? (size_t)sys * RT : 0);
+  double acc = 0.0, aq = 0.0, ae = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int nk = min(count[i * ld + sys], ntt_body[i]);
+    for (int k = 0; k < nk; ++k) {
+      const int slot = off[i] + k;
+      const double s = sg[slot], t = to[slot];
+      if (!(s > 0.0) || !isfinite(t)) continue;
+      const size_t rec = (size_t)sys * RT + slot;
+      const double r = (tt[rec] - t) / s;
+      acc = fma(r, r, acc);
+      const double w = 2.0 * r / s;
+      if (c < M) {
+        if (dtdq0 && gq) aq = fma(w, dtdq0[rec * M + c], aq);
+        if (dtde && ge) ae = fma(w, dtde[rec * M + c], ae);
+      }
+    }
+  }
+  if (c == 0) chi2[sys] = acc;
+  if (c < M) {
+    if (gq) gq[(size_t)sys * M + c] = aq;
+    if (ge) ge[(size_t)sys * M + c] = ae;
+  }
+}
+
 // ---- layout conversion kernels (host AoS <-> device SoA) ----
 __global__ void pack_xvm_kernel(const double* x, const double* v, const double* m, const double* xe, const double* ve, const double* dqdt,
                                 TrajArrays T, int n, long nsys, double t0) {
@@ -1281,6 +1317,35 @@ int32_t nbg_transit_fetch(nbg_plan* p, double* tt, int64_t* count, double* dtdq0
   if (dtdq0 && p->transit_grad) CK(cudaMemcpyAsync(dtdq0, p->bdtdq0.p, nsys * RT * M * C * 8, cudaMemcpyDeviceToHost, p->stream));
   if (dtdelements && p->have_dtde) CK(cudaMemcpyAsync(dtdelements, p->bdtde.p, nsys * RT * M * C * 8, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
+  return NBG_OK;
+}
+
+int32_t nbg_transit_chi2(nbg_plan* p, const double* t_obs, const double* sigma, int32_t per_system, double* chi2, double* grad_q0,
+                         double* grad_elements) {
+  if (!p || !p->have_transit) return fail(NBG_ERR_ARG, "no transit results");
+  if (!t_obs || !sigma || !chi2) return fail(NBG_ERR_ARG, "t_obs, sigma and chi2 are required");
+  if (p->C != 1) return fail(NBG_ERR_UNSUPPORTED, "chi^2 is defined for TransitTiming (mode 0) results");
+  if (grad_q0 && !p->transit_grad) return fail(NBG_ERR_ARG, "the last transit call ran with grad = 0");
+  if (grad_elements && !p->have_dtde) return fail(NBG_ERR_ARG, "no dtdelements (jac_init was not given)");
+  CK(cudaSetDevice(p->device));
+  const size_t nsys = p->nsys, M = 7 * (size_t)p->n, RT = p->RT, nobs = (per_system ? nsys : 1) * RT;
+  if (p->stage[0].ensure(std::max<size_t>(8, nobs * 8)) || p->stage[1].ensure(std::max<size_t>(8, nobs * 8)) || p->stage[2].ensure(nsys * 8) ||
+      p->stage[3].ensure(nsys * M * 8) || p->stage[4].ensure(nsys * M * 8))
+    return fail(NBG_ERR_NOMEM, "staging allocation failed");
+  CK(cudaMemcpyAsync(p->stage[0].p, t_obs, nobs * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->stage[1].p, sigma, nobs * 8, cudaMemcpyHostToDevice, p->stream));
+  const int threads = 32 * (int)((M + 31) / 32);
+  chi2_kernel<<<(unsigned)nsys, threads, 0, p->stream>>>(p->btt.as<double>(), p->transit_grad ? p->bdtdq0.as<double>() : nullptr,
+                                                          p->have_dtde ? p->bdtde.as<double>() : nullptr, p->bcount.as<int32_t>(), p->bntt.as<int32_t>(),
+                                                          p->boff.as<int32_t>(), p->n, p->ld, (int)RT, p->stage[0].as<double>(), p->stage[1].as<double>(),
+                                                          per_system ? 1 : 0, p->stage[2].as<double>(), grad_q0 ? p->stage[3].as<double>() : nullptr,
+                                                          grad_elements ? p->stage[4].as<double>() : nullptr);
+  p->launches++;
+  CK(cudaMemcpyAsync(chi2, p->stage[2].p, nsys * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (grad_q0) CK(cudaMemcpyAsync(grad_q0, p->stage[3].p, nsys * M * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (grad_elements) CK(cudaMemcpyAsync(grad_elements, p->stage[4].p, nsys * M * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  CK(cudaGetLastError());
   return NBG_OK;
 }
 

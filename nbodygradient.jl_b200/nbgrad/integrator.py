@@ -297,6 +297,19 @@ class Integrator:
                 if e_raw is not None:
                     tt.dtbvdelements[...] = e_raw.transpose(0, 5, 1, 2, 4, 3)
         self._timings(plan)
+        self._last_plan, self._last_tt = plan, tt
+
+    def chi2(self, t_obs, sigma):
+        """Fused transit-time likelihood on the device for the LAST (s, tt::TransitTiming) call of this Integrator (nbg_transit_chi2):
+        chi2[b] = sum ((tt - t_obs)/sigma)^2 and its gradients w.r.t. the initial Cartesian state [b,q,p] and the elements [b,q,p].
+        t_obs, sigma: [n, ntt] (shared by the batch) or [B, n, ntt]; sigma <= 0 or NaN t_obs = no observation in that slot."""
+        plan, tt = self._last_plan, self._last_tt
+        B, n, M = tt.nsys, tt.n, 7 * tt.n
+        t_obs = np.ascontiguousarray(t_obs, dtype=np.float64); sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+        per_system = 1 if t_obs.ndim == 3 else 0
+        chi2, gq, ge = np.zeros(B), np.zeros((B, n, 7)), np.zeros((B, n, 7))
+        check(_lib.lib().nbg_transit_chi2(plan, ptr(t_obs), ptr(sigma), C.c_int32(per_system), ptr(chi2), ptr(gq), ptr(ge)))
+        return chi2, gq.transpose(0, 2, 1).copy(), ge.transpose(0, 2, 1).copy()
 
 
 def device_count():

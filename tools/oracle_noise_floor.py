@@ -17,4 +17,4 @@ print('counts equal',np.array_equal(a['count'],b['count']), a['count'].sum())
 m=a['tt']!=0
 print('tt rel',np.max(np.abs(a['tt'][m]-b['tt'][m])/np.abs(a['tt'][m])))
 print('dtdq0 rel',rel(a['dtdq0'],b['dtdq0']),'dtdelements rel',rel(a['dtdelements'],b['dtdelements']))
-print('x rel',rel(a_s['x'],b_s['x']),'jac rel',rel(a_s['jac_step_cm'],b_s['jac_step_cm']))
+print('x rel',rel(a_s['x'],b_s['x']),'v rel',rel(a_s['v'],b_s['v']),'jac rel',rel(a_s['jac_step_cm'],b_s['jac_step_cm']))
