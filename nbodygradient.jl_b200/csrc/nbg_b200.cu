@@ -193,6 +193,10 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   for (int pre = 0; pre < npre; ++pre) dt0 = transit_pre_iteration<KICKS>(b0, n, dt0, ti, j, kmask);
   double tt1 = dt0 + 1.0, tt2 = dt0 + 2.0;
   int iter = 0;
+  // The final step at the converged dt0 (timing.jl:75-80) is always re-run with record emission.  (When the loop ends with
+  // dt0 == tt1 it repeats the last iteration bit for bit and could be skipped by emitting records inside the loop; measured on
+  // B200 that is slower -- 72 vs 65 ms per bench step for this kernel -- because every iteration then pays the 40 KB record write.)
+  Emit em{GRAD ? Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e) : nullptr, TILE, (size_t)(e % TILE)};
   while (true) {
     tt2 = tt1;
     tt1 = dt0;
@@ -206,9 +210,9 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
     if (iter >= 20 || dt0 == tt1 || dt0 == tt2) break;
   }
   uint32_t st = (iter >= 20) ? NBG_ST_TRANSIT_ITMAX : 0u;
-  if (GRAD) {
+  const bool redo = GRAD;
+  if (redo) {
     b = b0;
-    Emit em{Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
     ahl21_step<true, 1, KICKS>(b, dq, n, dt0, em, kmask);
   }
   const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
@@ -228,7 +232,8 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   if (st) atomicOr(&T.status[sys], st);
   atomicAdd(&counters[1], (unsigned long long)iter);
   atomicAdd(&counters[3], 1ull);
-  if (GRAD) atomicAdd(&counters[2], 1ull);
+  if (redo) atomicAdd(&counters[2], 1ull);
+  if (GRAD) atomicAdd(&counters[4], 1ull);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -666,7 +671,7 @@ struct nbg_plan {
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters, belem;
   DevBuf stage[8];  // staging for host<->device conversions
-  bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true;
+  bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
@@ -839,26 +844,27 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     p->launches++;
     // The operator kernels of the main steps (pair_op, phi_dense) depend only on the trajectory kernel; they run on the aux
     // stream next to the transit refinement (latency-bound, few threads) and join before the Jacobian kernel.
-    const bool fork = grad && (s_split > 0 || use_rx);
+    const bool fork = grad && (s_split > 0 || use_rx) && p->overlap;
+    cudaStream_t aux = p->overlap ? p->aux_stream : p->stream;
     if (fork) {
       CK(cudaEventRecord(p->ev_traj, p->stream));
       CK(cudaStreamWaitEvent(p->aux_stream, p->ev_traj, 0));
     }
     if (s_split > 0) {
-      tm.begin(6, p->aux_stream);
+      tm.begin(6, aux);
       const int py = 4;
       const dim3 grid((unsigned)(ld / TILE), (unsigned)s_split, (unsigned)((2 * npairs(n) + py - 1) / py)), block(TILE, py);
-      pair_op_kernel<<<grid, block, 0, p->aux_stream>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys);
+      pair_op_kernel<<<grid, block, 0, aux>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys);
       tm.end();
       p->launches++;
     }
     if (grad && use_rx) {
-      tm.begin(5, p->aux_stream);
-      if (launch_phi_dense(p->aux_stream, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      tm.begin(5, aux);
+      if (launch_phi_dense(aux, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
       tm.end();
       p->launches++;
     }
-    if (fork) CK(cudaEventRecord(p->ev_ops, p->aux_stream));
+    if (fork) CK(cudaEventRecord(p->ev_ops, aux));
     if (detect) {
       tm.begin(1);
       const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
@@ -984,6 +990,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
+  if (const char* e = getenv("NBG_OVERLAP")) p->overlap = (e[0] != '0');   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
   if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
@@ -1191,7 +1198,7 @@ static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);
-  for (int q = 1; q <= 3; ++q) p->counters_host[q] = dc[q];
+  for (int q = 1; q <= 4; ++q) p->counters_host[q] = dc[q];
   p->counters_host[5] = p->counters_host[5];
 }
 
@@ -1365,7 +1372,7 @@ int32_t nbg_counters(nbg_plan* p, int64_t* c8) {
   if (!p || !c8) return fail(NBG_ERR_ARG, "NULL argument");
   for (int q = 0; q < 8; ++q) c8[q] = (int64_t)p->counters_host[q];
   c8[4] = p->launches;
-  c8[5] = (int64_t)(p->counters_host[5] + p->counters_host[2]);
+  c8[5] = (int64_t)(p->counters_host[5] + p->counters_host[4]);
   return NBG_OK;
 }
 int32_t nbg_counters_reset(nbg_plan* p) {
