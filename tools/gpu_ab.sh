@@ -1,6 +1,6 @@
 # A/B of two prebuilt libraries (libA.so = HEAD, libB.so = working tree), operator kernels serialized for clean per-kernel times
 for L in /root/repo/libA.so /root/repo/libB.so; do
-NBG_OVERLAP=0 NBGRAD_B200_LIB=$L timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err
+NBG_OVERLAP=${OVL:-1} NBGRAD_B200_LIB=$L timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err
 python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_ab.json'))
