@@ -89,6 +89,12 @@ int32_t nbg_get_jac_init(nbg_plan* plan, double* jac_init);
  * time_mode 0: s.t += Kahan sum of h per step ((intr)(s,N), Integrator.jl:229); 1: s.t = t_final. */
 int32_t nbg_integrate_resident(nbg_plan* plan, double h, int64_t nsteps, double h_last, int32_t grad, int32_t time_mode, double t_final);
 
+/* (intr)(s, o::CartesianOutput) (src/outputs/Outputs.jl:26-49): nsteps steps of size h from the resident state (s.t = t0 + h i);
+ * x, v BEFORE every `stride`-th step (Outputs.jl:40 saves the state before the step) are returned as
+ * x_samples[k][sys][body][3], k = 0 .. ceil(nsteps/stride)-1.  The reference also keeps jac_step per saved State; here the
+ * Jacobian is available at the end (nbg_get_state), or per sample by cutting the integration into calls. */
+int32_t nbg_integrate_sampled(nbg_plan* plan, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples);
+
 /* One-shot form with HOST buffers: set_state + integrate + get_state. */
 int32_t nbg_integrate(nbg_plan* plan, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0, double h,
                       int64_t nsteps, double h_last, int32_t grad, double* x, double* v, double* xerror, double* verror,

@@ -41,6 +41,9 @@ struct TrajArrays {
   int32_t* count;
   uint32_t* status;
   size_t ld;  // padded system count (leading dimension of every SoA array)
+  // CartesianOutput-style sampling (Outputs.jl:26-49): x, v BEFORE every samp_stride-th step, [sample][3n][ld]; null = off
+  double *samp_x = nullptr, *samp_v = nullptr;
+  long samp_stride = 1;
 };
 
 struct EventQueue {
@@ -86,6 +89,10 @@ __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel
   uint32_t st = 0;
   const size_t sf = step_fields(n, kmask != 0u);
   for (int s = 0; s < nsteps; ++s) {
+    if (T.samp_x && (istep0 + s) % T.samp_stride == 0) {  // o.states[i] = deepcopy(s) before the step (Outputs.jl:40)
+      const size_t k = (size_t)((istep0 + s) / T.samp_stride);
+      for (int q = 0; q < 3 * n; ++q) { T.samp_x[(k * 3 * n + q) * ld + sys] = b.x[q]; T.samp_v[(k * 3 * n + q) * ld + sys] = b.v[q]; }
+    }
     Emit em{EMIT ? stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys) : nullptr, TILE, (size_t)(sys % TILE),
             EMIT == 2 ? scal + tile_offset((size_t)2 * npairs(n) * SCF, ld / TILE, (size_t)s, (size_t)sys) : nullptr};
     ahl21_step<GRAD, EMIT, KICKS>(b, dq, n, h, em, kmask);
@@ -621,6 +628,13 @@ __global__ void jac_from_julia_kernel(const double* in, double* J6, int n, int i
     else val = (!is_error && (7 * b + k) == col) ? 1.0 : 0.0;
     J6[(size_t)sys * 6 * n * M + q] = val;
   }
+}
+// [sample][3n][ld] -> [sample][sys][body][3]
+__global__ void unpack_samples_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, long nsys, size_t ld, long nsamp) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long k = blockIdx.y;
+  if (sys >= nsys || k >= nsamp) return;
+  for (int q = 0; q < 3 * n; ++q) dst[((size_t)k * nsys + sys) * 3 * n + q] = src[((size_t)k * 3 * n + q) * ld + sys];
 }
 __global__ void count_out_kernel(const int32_t* count, size_t ld, int n, long nsys, int64_t* out) {
   const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1224,6 +1238,49 @@ int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_l
   CK(cudaStreamSynchronize(p->stream));
   finish_timings(p, tm, e0, e1);
   CK(cudaGetLastError());
+  return NBG_OK;
+}
+
+// (intr)(s, o::CartesianOutput) (Outputs.jl:26-49) without the per-step host round trip: positions and velocities before every
+// `stride`-th step are collected on the device and copied out once.
+int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples) {
+  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  if (nsteps < 1 || stride < 1 || !x_samples || !v_samples) return fail(NBG_ERR_ARG, "nsteps >= 1, stride >= 1 and both sample buffers are required");
+  CK(cudaSetDevice(p->device));
+  const size_t n = p->n, nsys = p->nsys, ld = p->ld;
+  const long nsamp = (long)((nsteps + stride - 1) / stride);
+  DevBuf sx, sv, ox;
+  if (sx.ensure((size_t)nsamp * 3 * n * ld * 8) || sv.ensure((size_t)nsamp * 3 * n * ld * 8) || ox.ensure((size_t)nsamp * 3 * n * nsys * 8)) {
+    sx.release(); sv.release(); ox.release();
+    return fail(NBG_ERR_NOMEM, "sample buffers do not fit (reduce nsteps / stride or the batch)");
+  }
+  double t0 = 0;
+  CK(cudaMemcpy(&t0, p->bt.p, 8, cudaMemcpyDeviceToHost));
+  if (grad) if (int r = make_jac_identity(p)) { sx.release(); sv.release(); ox.release(); return r; }
+  p->T.samp_x = sx.as<double>(); p->T.samp_v = sv.as<double>(); p->T.samp_stride = (long)stride;
+  Timer tm{p->stream};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, p->stream);
+  // s.t[1] = t0 + h i (Outputs.jl:43): same time bookkeeping as the transit driver
+  const int rc = run_steps(p, h, (long)nsteps, grad != 0, false, 0, t0, h, false, tm, 0.0);
+  p->T.samp_x = nullptr; p->T.samp_v = nullptr;
+  cudaEventRecord(e1, p->stream);
+  cudaStreamSynchronize(p->stream);
+  finish_timings(p, tm, e0, e1);
+  if (rc) { sx.release(); sv.release(); ox.release(); return rc; }
+  const dim3 grid((unsigned)((nsys + 127) / 128), (unsigned)nsamp);
+  double* outs[2] = {x_samples, v_samples};
+  const double* srcs[2] = {sx.as<double>(), sv.as<double>()};
+  for (int q = 0; q < 2; ++q) {
+    unpack_samples_kernel<<<grid, 128, 0, p->stream>>>(srcs[q], ox.as<double>(), (int)n, (long)nsys, ld, nsamp);
+    p->launches++;
+    cudaMemcpyAsync(outs[q], ox.p, (size_t)nsamp * 3 * n * nsys * 8, cudaMemcpyDeviceToHost, p->stream);
+    cudaStreamSynchronize(p->stream);
+  }
+  const cudaError_t err = cudaGetLastError();
+  sx.release(); sv.release(); ox.release();
+  if (err != cudaSuccess) return fail(NBG_ERR_CUDA, cudaGetErrorString(err));
   return NBG_OK;
 }
 

@@ -200,6 +200,15 @@ class TransitParameters(_TransitOutput):
         self.dtbvdelements = np.zeros((B, 3, n, ntt, 7, n))
 
 
+class CartesianOutput:
+    """CartesianOutput(nbody, nstep) -- Outputs.jl:7-17.  The reference deep-copies the whole State before every step; here x and v
+    before every `stride`-th step are collected on the device (nbg_integrate_sampled): o.x[k, b, i, :], o.v[k, b, i, :], o.t[k]."""
+
+    def __init__(self, nbody, nstep, stride=1):
+        self.nbody, self.nstep, self.stride = int(nbody), int(nstep), int(stride)
+        self.x = self.v = self.t = None
+
+
 class Integrator:
     """Integrator(h, tmax) | Integrator(h, t0, tmax) | Integrator(scheme, h, t0, tmax) — Integrator.jl:17-31."""
 
@@ -230,6 +239,8 @@ class Integrator:
     def __call__(self, s, arg=None, grad=True):
         if isinstance(arg, _TransitOutput):
             return self._transits(s, arg, grad)
+        if isinstance(arg, CartesianOutput):
+            return self._sampled(s, arg, grad)
         if isinstance(arg, (int, np.integer)) and not isinstance(arg, bool):
             return self._nsteps(s, int(arg), grad)
         if arg is None:
@@ -259,6 +270,20 @@ class Integrator:
         s._upload(plan, grad)
         check(_lib.lib().nbg_integrate_resident(plan, C.c_double(h), C.c_int64(N), C.c_double(0.0), C.c_int32(1 if grad else 0), C.c_int32(0),
                                                 C.c_double(0.0)))
+        s._download(plan, grad)
+        self._timings(plan)
+
+    # (intr)(s, o::CartesianOutput) — Outputs.jl:26-49
+    def _sampled(self, s, o, grad):
+        t0 = float(s.t[0])
+        h = self.h * check_step(t0, self.tmax)
+        ns = (o.nstep + o.stride - 1) // o.stride
+        plan = self._p(s)
+        s._upload(plan, grad)
+        o.x, o.v = np.zeros((ns, s.nsys, s.n, 3)), np.zeros((ns, s.nsys, s.n, 3))
+        o.t = t0 + h * o.stride * np.arange(ns)
+        check(_lib.lib().nbg_integrate_sampled(plan, C.c_double(h), C.c_int64(o.nstep), C.c_int64(o.stride), C.c_int32(1 if grad else 0),
+                                               ptr(o.x), ptr(o.v)))
         s._download(plan, grad)
         self._timings(plan)
 

@@ -438,3 +438,24 @@ def test_fused_chi2_and_gradients(nb, elements):
         assert rel(gq, np.einsum("bik,bikqp->bqp", w, tt.dtdq0)) < 1e-12
         assert rel(ge, np.einsum("bik,bikqp->bqp", w, tt.dtdelements)) < 1e-12
     assert chi2.min() > 1.0
+
+
+def test_cartesian_output_sampling(nb, oracle, elements):
+    # (intr)(s, o::CartesianOutput) -- the state saved BEFORE each step (Outputs.jl:40), here every 5th, collected on
+    # the device; against the oracle stepped to the same instants, and the final state/time as in the reference (s.t = t0 + h i).
+    n, t0, h, nstep, stride = 4, 7257.0, 0.05, 43, 5
+    ic = nb.ElementsIC(t0, n, elements)
+    s, o = nb.State(ic), nb.CartesianOutput(n, nstep, stride)
+    nb.Integrator(h, t0 + 1000.0)(s, o)     # Outputs.jl:32-33: direction from check_step(t0, intr.tmax), tmax as an absolute time
+    assert o.x.shape == (9, 1, n, 3)
+    x, v, _ = oracle.init_nbody(elements[:n], t0)
+    so = oracle.new_state(x, v, elements[:n, 0], t0)
+    done = 0
+    for k in range(o.x.shape[0]):
+        oracle.integrate(so, h, nsteps=k * stride - done, grad=True) if k * stride > done else None
+        done = k * stride
+        assert rel(o.x[k, 0], so["x"]) < TOL and rel(o.v[k, 0], so["v"]) < TOL
+        assert abs(o.t[k] - (t0 + h * k * stride)) < 1e-12
+    oracle.integrate(so, h, nsteps=nstep - done, grad=True)
+    assert rel(s.x[0], so["x"]) < TOL and rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+    assert abs(s.t[0] - (t0 + h * nstep)) < 1e-9
