@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   int iter = 0;
   // The final step at the converged dt0 (timing.jl:75-80) is always re-run with record emission.  (When the loop ends with
   // dt0 == tt1 it repeats the last iteration bit for bit and could be skipped by emitting records inside the loop; measured on
-  // B200 that is slower -- 72 vs 65 ms per bench step for this kernel -- because every iteration then pays the 40 KB record write.)
+  // B200 that is slower -- 72 vs 65 ms per bench step for this kernel with full records, 69 with only the 14 KB of scalars that
+  // pair_op_kernel needs -- the iterations, already at 255 registers with spills, get slower by more than the saved step.)
   Emit em{GRAD ? Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e) : nullptr, TILE, (size_t)(e % TILE)};
   while (true) {
     tt2 = tt1;
