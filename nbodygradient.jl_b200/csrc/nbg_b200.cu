@@ -492,12 +492,9 @@ int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jb
                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
   const size_t smem = ((size_t)2 * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0)) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
-  }
+  // per launch, not once: function attributes are per device, and plans of one process may live on different devices
+  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O,
                                                                                      kmask);
   return 0;
