@@ -309,20 +309,30 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 // register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
-__global__ void __launch_bounds__(rx_warps(N) * 32, MB)
+// SPB systems per block (1 or 2).  With 2, the two systems' warps that share an SM sub-partition run the same straight-line
+// instruction stream side by side (one barrier pattern per work item for both), so they share instruction fetches: the fully
+// unrolled step is 85 KB of code, executed once per step and warp, and instruction fetch is the kernel's top stall (ncu r01h).
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, int SPB = 1>
+__global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
-                  int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
-                  uint32_t kmask) {
+                  int nsteps_in, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
+                  uint32_t kmask, long nsys) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int NS = KICK ? 3 : 1;  // dense operators per step (nbg_kicks.cuh)
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + NS * PF) + NS * 12 * N * N /* stream */,
                 SB = 2 * P * KF + NS * 12 * N * N /* staged */, G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + NS * PF) / 4, G1 = NS * 3 * N * N,
                 NT = rx_warps(N) * 32;
+  static_assert(SPB == 1 || !KICK, "the fast-kick variant runs one system per block");
+  const int slot_in_block = SPB == 1 ? 0 : (int)threadIdx.x / NT;
+  const int tid = SPB == 1 ? (int)threadIdx.x : (int)threadIdx.x % NT;
+  double* const smsys = smrx + (size_t)slot_in_block * 2 * SB;
   double* const hold = smrx + 2 * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
-  const long sys = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, c = warp * 16 + (lane & 15);
-  const bool valid = c < M;
+  const long sys_raw = (long)blockIdx.x * SPB + slot_in_block;
+  const bool live = sys_raw < nsys;            // odd batch: the last block's second slot only takes part in the barriers
+  const long sys = live ? sys_raw : nsys - 1;
+  const int nsteps = live ? nsteps_in : 0;
+  const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, c = warp * 16 + (lane & 15);
+  const bool valid = c < M && live;
   RxState<N> S;
 #pragma unroll
   for (int b = 0; b < N; ++b)
@@ -332,10 +342,10 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       S.jv[b][k] = valid ? Jv_g[q] : 0.0;
       S.je[b][k] = valid ? Je_g[q] : 0.0;
     }
-  double* const buf0 = smrx;
-  double* const buf1 = smrx + SB;
+  double* const buf0 = smsys;
+  double* const buf1 = smsys + SB;
   const size_t ntiles = ld / TILE;
-  rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+  if (live) rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
   // One loop over work items -- a main step, or the extra step of a queued transit -- so that rx_step<N> (13k
   // instructions, fully unrolled) exists once in the instruction stream.
   double* const bk = Jbak + (size_t)sys * 6 * N * NT + tid;
@@ -347,13 +357,20 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
   while (true) {
     double* const cur = (s & 1) ? buf1 : buf0;
     double h2;
+    const bool fin = !in_event && s >= nsteps;
+    if (SPB == 1) {
+      if (fin) break;
+    } else {  // every work item has the same barrier pattern (two), whatever its kind, so the systems of a block stay side by side
+      if (__syncthreads_and(fin)) break;
+      if (fin) { __syncthreads(); __syncthreads(); continue; }
+    }
     if (!in_event) {
-      if (s >= nsteps) break;
       pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
       __pipeline_wait_prior(0);
       __syncthreads();  // step s operators visible; everyone is done with the other buffer
       if (s + 1 < nsteps)
         rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+      if (SPB > 1) __syncthreads();
       h2 = 0.5 * h;
     } else {
       __syncthreads();  // everyone is done with cur
@@ -487,16 +504,16 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
   return 0;
 }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, int SPB = 1>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
-  const size_t smem = ((size_t)2 * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0)) * 8;
+  const size_t smem = ((size_t)2 * SB * SPB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0)) * 8;
   // per launch, not once: function attributes are per device, and plans of one process may live on different devices
-  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O,
-                                                                                     kmask);
+  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, SPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, SPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  jac_rx_kernel<N, U, SYNC, MB, KICK, SPB><<<(unsigned)((nsys + SPB - 1) / SPB), rx_warps(N) * 32 * SPB, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h,
+                                                                                                                    evlist, evmask, Q, ti, O, kmask, nsys);
   return 0;
 }
 // fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
@@ -922,6 +939,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             else if (p->rx_unroll == 32) rc = launch_jac_rx<8, 2, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
             else if (p->rx_unroll == 18) rc = launch_jac_rx<8, 8, false, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
             else if (p->rx_unroll == 34) rc = launch_jac_rx<8, 4, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else if (p->rx_unroll == 48) rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
             else if (p->rx_unroll == 38) rc = launch_jac_rx<8, 8, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
             else rc = launch_jac_rx<8, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
             break;
