@@ -737,6 +737,16 @@ size_t jac_smem_bytes(int n, bool stage_phi) {
   return d * 8;
 }
 
+// a pair of timing events that is destroyed on every exit path
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool live = true;
+  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EventPair() { if (live) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+};
+
 struct Timer {
   cudaStream_t s;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
@@ -749,6 +759,7 @@ struct Timer {
     ev.push_back({kind, {a, b}});
   }
   void end() { cudaEventRecord(ev.back().second.second, cur); }
+  ~Timer() { for (auto& e : ev) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); } }
   void collect(double* ms4) {
     for (auto& e : ev) {
       float t = 0;
@@ -1005,6 +1016,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   nbg_plan* p = new nbg_plan();
   p->n = nbody; p->nsys = nsys; p->device = device;
   p->ld = (size_t)((nsys + 31) / 32 * 32);
+  struct Guard { nbg_plan* p; ~Guard() { if (p) nbg_plan_destroy(p); } } guard{p};  // releases everything on an early return
   CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&p->copy_done, cudaEventDisableTiming));
@@ -1022,8 +1034,9 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
   if (const char* e = getenv("NBG_OVERLAP")) p->overlap = (e[0] != '0');   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
-  if (alloc_state(p)) { delete p; return fail(NBG_ERR_NOMEM, "state allocation failed"); }
+  if (alloc_state(p)) return fail(NBG_ERR_NOMEM, "state allocation failed");
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
+  guard.p = nullptr;
   *out = p;
   return NBG_OK;
 }
@@ -1031,17 +1044,21 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
 int32_t nbg_plan_destroy(nbg_plan* p) {
   if (!p) return NBG_OK;
   cudaSetDevice(p->device);
-  cudaStreamSynchronize(p->stream);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+  if (p->aux_stream) cudaStreamSynchronize(p->aux_stream);
   DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
                    &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
                    &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters, &p->belem};
   for (auto* b : all) b->release();
   for (auto& b : p->stage) b.release();
-  cudaStreamDestroy(p->stream);
-  cudaStreamDestroy(p->copy_stream);
-  cudaEventDestroy(p->copy_done);
-  cudaStreamDestroy(p->aux_stream);
-  cudaEventDestroy(p->ev_traj); cudaEventDestroy(p->ev_ops);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  if (p->copy_done) cudaEventDestroy(p->copy_done);
+  if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+  if (p->ev_traj) cudaEventDestroy(p->ev_traj);
+  if (p->ev_ops) cudaEventDestroy(p->ev_ops);
+  cudaGetLastError();
   delete p;
   return NBG_OK;
 }
@@ -1216,7 +1233,8 @@ int32_t nbg_get_state(nbg_plan* p, double* x, double* v, double* xerror, double*
   return NBG_OK;
 }
 
-static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e1) {
+static void finish_timings(nbg_plan* p, Timer& tm, EventPair& ev) {
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   for (double& q : p->timings) q = 0;
   tm.collect(p->timings);
   float tot = 0;
@@ -1225,7 +1243,6 @@ static void finish_timings(nbg_plan* p, Timer& tm, cudaEvent_t e0, cudaEvent_t e
   // pair_op / phi_dense run on the aux stream concurrently with the transit kernel, so the per-kernel times can add up to more
   // than the total; "other" is what is left of the total, never negative
   p->timings[3] = std::max(0.0, tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6]);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);
   for (int q = 1; q <= 4; ++q) p->counters_host[q] = dc[q];
@@ -1239,8 +1256,8 @@ int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_l
   if (grad) if (int r = make_jac_identity(p)) return r;
   if (time_mode == 0) CK(cudaMemsetAsync(p->bterr.p, 0, p->ld * 8, p->stream));  // s2 = zero(T): Integrator.jl:212
   Timer tm{p->stream};
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaEventRecord(e0, p->stream);
   if (int r = run_steps(p, h, (long)nsteps, grad != 0, false, 0, 0.0, h, time_mode == 0, tm, 0.0)) return r;
   if (h_last != 0.0)
@@ -1252,7 +1269,7 @@ int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_l
   }
   cudaEventRecord(e1, p->stream);
   CK(cudaStreamSynchronize(p->stream));
-  finish_timings(p, tm, e0, e1);
+  finish_timings(p, tm, ev);
   CK(cudaGetLastError());
   return NBG_OK;
 }
@@ -1275,15 +1292,15 @@ int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t str
   if (grad) if (int r = make_jac_identity(p)) { sx.release(); sv.release(); ox.release(); return r; }
   p->T.samp_x = sx.as<double>(); p->T.samp_v = sv.as<double>(); p->T.samp_stride = (long)stride;
   Timer tm{p->stream};
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaEventRecord(e0, p->stream);
   // s.t[1] = t0 + h i (Outputs.jl:43): same time bookkeeping as the transit driver
   const int rc = run_steps(p, h, (long)nsteps, grad != 0, false, 0, t0, h, false, tm, 0.0);
   p->T.samp_x = nullptr; p->T.samp_v = nullptr;
   cudaEventRecord(e1, p->stream);
   cudaStreamSynchronize(p->stream);
-  finish_timings(p, tm, e0, e1);
+  finish_timings(p, tm, ev);
   if (rc) { sx.release(); sv.release(); ox.release(); return rc; }
   const dim3 grid((unsigned)((nsys + 127) / 128), (unsigned)nsamp);
   double* outs[2] = {x_samples, v_samples};
@@ -1343,8 +1360,8 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   const long nsteps = std::labs((long)std::nearbyint(tmax / h));         // Transits.jl:143
   const double hs = h * check_step(t0, tmax + t0);                       // Transits.jl:144
   Timer tm{p->stream};
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaEventRecord(e0, p->stream);
   const int tpb = 128;
   gsave_init_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T, n, (long)nsys, ti);
@@ -1377,7 +1394,7 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   }
   cudaEventRecord(e1, p->stream);
   CK(cudaStreamSynchronize(p->stream));
-  finish_timings(p, tm, e0, e1);
+  finish_timings(p, tm, ev);
   CK(cudaGetLastError());
   return NBG_OK;
 }
