@@ -305,8 +305,9 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   for (size_t q = tid; q < jsz; q += nthr) { Jv_g[sys * jsz + q] = S.Jv[q]; Je_g[sys * jsz + q] = S.Je[q]; }
 }
 
-// Register-resident Jacobian kernel (N <= 8): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
-// register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM
+// Register-resident Jacobian kernel (N <= NBG_RX_MAX_BODIES = 12): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
+// register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM;
+// N = 9: 2 blocks of 4 warps at 255 registers; N = 10..12: one block of 5-6 warps per SM (255 registers, 109-163 KB of operator ring)
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
 // SPB systems per block (1 or 2).  With 2, the two systems' warps that share an SM sub-partition run the same straight-line
@@ -484,7 +485,8 @@ __global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(doubl
   if (idx >= nv) return;
   double* blk = base + tile_offset(step_fields(N, kicked != 0), ntiles, blockIdx.y, (size_t)idx);
   if (!kicked) phi_dense_rows<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y);
-  else phi_dense_rows_kicked<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y, phi_rec_offset(N, blockIdx.z), phi_dense_offset(N, true, blockIdx.z));
+  else if constexpr (N <= 8)  // fast-kick pairs exist for N <= 8 only (pair mask in 32 bits)
+    phi_dense_rows_kicked<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y, phi_rec_offset(N, blockIdx.z), phi_dense_offset(N, true, blockIdx.z));
 }
 // main steps: ntiles = ld / 32, nsteps steps; queued transits: ntiles = 0 (one "step"), nitems_dev = device count of queued transits
 int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long nitems, const int32_t* nitems_dev, int nsteps, bool kicked = false) {
@@ -499,6 +501,10 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
     case 6: phi_dense_kernel<6><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 7: phi_dense_kernel<7><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 8: phi_dense_kernel<8><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 9: phi_dense_kernel<9><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 10: phi_dense_kernel<10><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 11: phi_dense_kernel<11><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 12: phi_dense_kernel<12><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     default: return -1;
   }
   return 0;
@@ -829,7 +835,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     const size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
     if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
-  const bool use_rx = n <= 8 && (!p->force_generic_jac || kicks);
+  const bool use_rx = n <= NBG_RX_MAX_BODIES && (!p->force_generic_jac || kicks);
   if (kicks && n > 8) return fail(NBG_ERR_UNSUPPORTED, "fast-kick pairs (s.pair) are supported for nbody <= 8");
   const int tpb = 128;
   const unsigned gridA = (unsigned)((nsys + tpb - 1) / tpb);
@@ -940,6 +946,13 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
           case 5: rc = launch_jac_rx<5, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 6: rc = launch_jac_rx<6, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 7: rc = launch_jac_rx<7, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 9: rc = launch_jac_rx<9, 1, true, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 10:  // NBG_RX_UNROLL=22: two blocks of 5 warps per SM at 168 registers (spills ~45 doubles) instead of one at 255
+            if (p->rx_unroll == 22) rc = launch_jac_rx<10, 1, true, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            else rc = launch_jac_rx<10, 1, true, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
+            break;
+          case 11: rc = launch_jac_rx<11, 1, true, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 12: rc = launch_jac_rx<12, 1, true, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
           default:
             // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
             if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);

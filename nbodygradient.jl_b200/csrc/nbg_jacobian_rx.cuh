@@ -1,5 +1,6 @@
-// Register-resident Jacobian propagation for N <= 8 bodies (the production path; nbg_jacobian.cuh is the generic
-// shared-memory version used for larger N).
+// Register-resident Jacobian propagation for N <= 12 bodies (the production path; nbg_jacobian.cuh is the generic
+// shared-memory version used for N = 13..16, where 12 N doubles of resident state per thread no longer fit in 255 registers
+// and a double-buffered operator block no longer fits in 227 KB of shared memory).
 //
 // Why this shape (measured on B200, profiles/microbench/r01_smem_fp64_probe.txt): per SM and per cycle the machine
 // issues 2 warp-DFMA, delivers ONE broadcast double from shared memory (LDS.64/.128 uniform or two addresses split by
@@ -25,6 +26,7 @@
 namespace nbg {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int NBG_RX_MAX_BODIES = 12;  // largest N with jac_step + jac_error in registers and a double-buffered operator block in shared memory
 __host__ __device__ constexpr int rx_warps(int n) { return (7 * n + 15) / 16; }
 
 __device__ __forceinline__ double shx(double v) { return __shfl_xor_sync(FULL, v, 16); }

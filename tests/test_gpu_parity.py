@@ -111,7 +111,7 @@ def test_resume_equals_single_run(nb, elements):
     assert np.array_equal(a.jac_step, b.jac_step) and np.array_equal(a.jac_error, b.jac_error)
 
 
-@pytest.mark.parametrize("n", [2, 3, 5, 8, 12, 16])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16])
 def test_nbody_sweep(nb, oracle, n):
     # cfg 4 at test size: star + (n-1) planets m=3e-5, P_k = 1.5*1.6^(k-1), nested hierarchy, h=0.05, 40 steps, grad
     el = np.zeros((n, 7)); el[0, 0] = 1.0
@@ -138,6 +138,30 @@ def _cmp_tt(tt_gpu, count_gpu, r):
     mask = r["tt"] != 0
     assert np.array_equal(mask, tt_gpu != 0)
     assert np.max(np.abs(tt_gpu[mask] - r["tt"][mask]) / np.abs(r["tt"][mask])) < TOL
+
+
+@pytest.mark.parametrize("n", [10, 12, 13])
+def test_transit_timing_above_8_bodies(nb, oracle, n):
+    # transit detection, Newton refinement and dtdq0 / dtdelements on the cfg 4 systems with more than 8 bodies: n <= 12 runs
+    # the register-resident Jacobian kernel (with queued transit steps), n = 13 the shared-memory one
+    el = np.zeros((n, 7)); el[0, 0] = 1.0
+    for k in range(1, n):
+        el[k] = [3e-5, 1.5 * 1.6 ** (k - 1), 0.1 * k, 0.01, 0.0, np.pi / 2, 0.0]
+    B = 3
+    elb = np.broadcast_to(el, (B, n, 7)).copy()
+    elb[1:, 1:, 1] *= 1 + 1e-4 * np.random.default_rng(n).standard_normal((B - 1, n - 1))
+    h, tmax = 0.05, 5.0
+    ic = nb.ElementsIC(0.0, n, elb)
+    s = nb.State(ic)
+    tt = nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s, tt)
+    assert int(tt.count.sum()) >= 3 * B
+    for b in range(B):
+        so, r = _tt_oracle(oracle, elb[b], 0.0, h, tmax, tt.ntt)
+        _cmp_tt(tt.tt[b], tt.count[b], r)
+        assert rel(tt.dtdq0[b], r["dtdq0"]) < TOL
+        assert rel(tt.dtdelements[b], r["dtdelements"]) < TOL
+        assert rel(s.x[b], so["x"]) < TOL and rel(s.jac_step[b], so["jac_step_cm"].T) < TOL
 
 
 def test_transit_timing_cfg1(nb, oracle, elements):
