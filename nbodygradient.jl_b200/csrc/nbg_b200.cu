@@ -317,7 +317,7 @@ template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK 
 __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
                   int nsteps_in, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
-                  uint32_t kmask, long nsys) {
+                  uint32_t kmask, long nsys, long sys0) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int NS = KICK ? 3 : 1;  // dense operators per step (nbg_kicks.cuh)
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + NS * PF) + NS * 12 * N * N /* stream */,
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
   const int tid = SPB == 1 ? (int)threadIdx.x : (int)threadIdx.x % NT;
   double* const smsys = smrx + (size_t)slot_in_block * 2 * SB;
   double* const hold = smrx + 2 * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
-  const long sys_raw = (long)blockIdx.x * SPB + slot_in_block;
+  const long sys_raw = sys0 + (long)blockIdx.x * SPB + slot_in_block;   // the launch covers systems sys0 .. nsys-1 (a slice of the batch)
   const bool live = sys_raw < nsys;            // odd batch: the last block's second slot only takes part in the barriers
   const long sys = live ? sys_raw : nsys - 1;
   const int nsteps = live ? nsteps_in : 0;
@@ -505,6 +505,8 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
     case 10: phi_dense_kernel<10><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 11: phi_dense_kernel<11><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 12: phi_dense_kernel<12><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 13: phi_dense_kernel<13><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 14: phi_dense_kernel<14><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     default: return -1;
   }
   return 0;
@@ -512,14 +514,14 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
 
 template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, int SPB = 1>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
-                  const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
+                  const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u, long sys0 = 0) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
   const size_t smem = ((size_t)2 * SB * SPB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0)) * 8;
   // per launch, not once: function attributes are per device, and plans of one process may live on different devices
   if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, SPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, SPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_rx_kernel<N, U, SYNC, MB, KICK, SPB><<<(unsigned)((nsys + SPB - 1) / SPB), rx_warps(N) * 32 * SPB, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h,
-                                                                                                                    evlist, evmask, Q, ti, O, kmask, nsys);
+  jac_rx_kernel<N, U, SYNC, MB, KICK, SPB><<<(unsigned)((nsys - sys0 + SPB - 1) / SPB), rx_warps(N) * 32 * SPB, smem, st>>>(
+      Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask, nsys, sys0);
   return 0;
 }
 // fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
@@ -539,10 +541,11 @@ int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* 
 
 // dtdelements = dtdq0 . jac_init  (calc_dtdelements!, timing.jl:112-138).  One block per (system, record tile).
 __global__ void dtdelements_kernel(const double* __restrict__ dtdq0, const double* __restrict__ jac_init, double* __restrict__ out,
-                                   const int32_t* __restrict__ count, const int32_t* ntt_body, const int32_t* off, int n, size_t ld, int RT, int C) {
+                                   const int32_t* __restrict__ count, const int32_t* ntt_body, const int32_t* off, int n, size_t ld, int RT, int C,
+                                   long sys0) {
   extern __shared__ double ji[];  // M x M column-major: ji[col*M + row]
   const int M = 7 * n;
-  const long sys = blockIdx.x;
+  const long sys = sys0 + blockIdx.x;
   for (int q = threadIdx.x; q < M * M; q += blockDim.x) ji[q] = jac_init[(size_t)sys * M * M + q];
   __syncthreads();
   for (int i = 0; i < n; ++i) {
@@ -717,6 +720,14 @@ struct nbg_plan {
   unsigned long long counters_host[8] = {0};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
+  // Host destinations of the transit outputs, known up front in the one-shot nbg_transit_timing call: the Jacobian kernel of the
+  // LAST chunk is launched in `slices` slices of the batch, and every finished slice (whose tt / dtdq0 rows are final) gets its
+  // dtdelements and its device-to-host copies on the copy stream while the next slice computes.
+  struct OutSink { double* tt = nullptr; double* dtdq0 = nullptr; double* dtde = nullptr; int slices = 0; bool want_dtde = false, delivered = false; };
+  OutSink sink;
+  int out_slices = 4;        // NBG_OUT_SLICES (<= 1: copy everything after the last kernel)
+  long out_slice_min = 4096; // NBG_OUT_SLICE_MIN: smallest batch that is sliced
+  std::vector<cudaEvent_t> ev_slice;   // one per slice, created on first use
 };
 
 namespace {
@@ -782,6 +793,26 @@ double check_step(double t0, double tmax) {  // Integrator.jl:249-259
   if (std::fabs(tmax) > std::fabs(t0)) return sg(tmax);
   if (sg(tmax) != sg(t0)) return sg(tmax);
   return -1 * sg(tmax);
+}
+
+// systems [lo, hi) are final: dtdelements for them, then their rows of tt / dtdq0 / dtdelements go to the host, all on the copy
+// stream (ordered after the jac_init upload that runs there), concurrently with the next slice's Jacobian kernel
+int deliver_slice(nbg_plan* p, int k, long lo, long hi) {
+  const size_t M = 7 * (size_t)p->n, C = p->C, RT = p->RT, cnt = (size_t)(hi - lo);
+  CK(cudaStreamWaitEvent(p->copy_stream, p->ev_slice[k], 0));
+  if (p->sink.want_dtde) {
+    CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * M * 8)));
+    dtdelements_kernel<<<(unsigned)cnt, 256, M * M * 8, p->copy_stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
+                                                                           p->bcount.as<int32_t>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->n, p->ld,
+                                                                           (int)RT, (int)C, lo);
+    p->launches++;
+  }
+  const size_t t0 = (size_t)lo * RT * C, q0 = t0 * M;
+  if (p->sink.tt) CK(cudaMemcpyAsync(p->sink.tt + t0, p->btt.as<double>() + t0, cnt * RT * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+  if (p->sink.dtdq0) CK(cudaMemcpyAsync(p->sink.dtdq0 + q0, p->bdtdq0.as<double>() + q0, cnt * RT * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+  if (p->sink.dtde && p->sink.want_dtde)
+    CK(cudaMemcpyAsync(p->sink.dtde + q0, p->bdtde.as<double>() + q0, cnt * RT * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+  return 0;
 }
 
 // core driver: runs `nsteps` steps of size h from the resident state in chunks.
@@ -938,35 +969,62 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>(), *Jb = p->bJbak.as<double>();
         const double* strm = p->bstream.as<double>();
         int rc = 0;
+        // last chunk of a call whose host outputs are known (p->sink): slices of the batch, each followed by its output copies
+        const int K = (p->sink.slices > 1 && detect && !kicks && done + s == nsteps) ? p->sink.slices : 1;
         if (kicks) rc = launch_jac_rx_kicked(n, p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, p->kmask);
-        else switch (n) {
-          case 2: rc = launch_jac_rx<2, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 3: rc = launch_jac_rx<3, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 4: rc = launch_jac_rx<4, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 5: rc = launch_jac_rx<5, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 6: rc = launch_jac_rx<6, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 7: rc = launch_jac_rx<7, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 9: rc = launch_jac_rx<9, 1, true, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 10:  // NBG_RX_UNROLL=22: two blocks of 5 warps per SM at 168 registers (spills ~45 doubles) instead of one at 255
-            if (p->rx_unroll == 22) rc = launch_jac_rx<10, 1, true, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else rc = launch_jac_rx<10, 1, true, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            break;
-          case 11: rc = launch_jac_rx<11, 1, true, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          case 12: rc = launch_jac_rx<12, 1, true, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O); break;
-          default:
-            // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
-            if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 12) rc = launch_jac_rx<8, 2, false>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 14) rc = launch_jac_rx<8, 4, false>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 22) rc = launch_jac_rx<8, 2, true, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 32) rc = launch_jac_rx<8, 2, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 18) rc = launch_jac_rx<8, 8, false, 3>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 34) rc = launch_jac_rx<8, 4, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 48) rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else if (p->rx_unroll == 38) rc = launch_jac_rx<8, 8, false, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            else rc = launch_jac_rx<8, 2>(p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O);
-            break;
+        else for (int k = 0; k < K && !rc; ++k) {
+          const long lo = (nsys / TILE) * k / K * TILE, hi = k + 1 == K ? nsys : (nsys / TILE) * (k + 1) / K * TILE;
+          if (hi <= lo) continue;
+          switch (n) {
+            case 2: rc = launch_jac_rx<2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 3: rc = launch_jac_rx<3, 3>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 4: rc = launch_jac_rx<4, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 5: rc = launch_jac_rx<5, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 6: rc = launch_jac_rx<6, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 7: rc = launch_jac_rx<7, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 9: rc = launch_jac_rx<9, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 10:  // two blocks of 5 warps per SM at 168 registers (spills ~45 doubles): measured 1.25x faster than one block at 255 (NBG_RX_UNROLL=21)
+              if (p->rx_unroll == 21) rc = launch_jac_rx<10, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else rc = launch_jac_rx<10, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              break;
+            case 11: rc = launch_jac_rx<11, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 12: rc = launch_jac_rx<12, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 13: rc = launch_jac_rx<13, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            case 14: rc = launch_jac_rx<14, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+            default:
+              // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
+              if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 12) rc = launch_jac_rx<8, 2, false>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 14) rc = launch_jac_rx<8, 4, false>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 22) rc = launch_jac_rx<8, 2, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 32) rc = launch_jac_rx<8, 2, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 18) rc = launch_jac_rx<8, 8, false, 3>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 34) rc = launch_jac_rx<8, 4, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 48) rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else if (p->rx_unroll == 38) rc = launch_jac_rx<8, 8, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              else rc = launch_jac_rx<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              break;
+          }
+          if (!rc && K > 1) {
+            while ((int)p->ev_slice.size() <= k) {
+              cudaEvent_t e;
+              CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+              p->ev_slice.push_back(e);
+            }
+            CK(cudaEventRecord(p->ev_slice[k], p->stream));
+          }
+        }
+        if (K > 1 && !rc) {
+          // every slice is in flight before the first copy is issued: a pageable destination makes cudaMemcpyAsync block the host,
+          // which must not delay the launches
+          tm.end();
+          for (int k = 0; k < K; ++k) {
+            const long lo = (nsys / TILE) * k / K * TILE, hi = k + 1 == K ? nsys : (nsys / TILE) * (k + 1) / K * TILE;
+            if (hi > lo) if (int r = deliver_slice(p, k, lo, hi)) return r;
+          }
+          tm.begin(2);
+          p->sink.delivered = true;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
       } else {
@@ -1047,6 +1105,8 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
   if (const char* e = getenv("NBG_OVERLAP")) p->overlap = (e[0] != '0');   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
+  if (const char* e = getenv("NBG_OUT_SLICES")) p->out_slices = std::max(1, std::min(64, atoi(e)));
+  if (const char* e = getenv("NBG_OUT_SLICE_MIN")) p->out_slice_min = std::max(1L, atol(e));
   if (alloc_state(p)) return fail(NBG_ERR_NOMEM, "state allocation failed");
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   guard.p = nullptr;
@@ -1071,6 +1131,8 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
   if (p->ev_traj) cudaEventDestroy(p->ev_traj);
   if (p->ev_ops) cudaEventDestroy(p->ev_ops);
+  for (cudaEvent_t e : p->ev_slice) cudaEventDestroy(e);
+  p->ev_slice.clear();
   cudaGetLastError();
   delete p;
   return NBG_OK;
@@ -1392,16 +1454,22 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
   }
   double rate = nsteps > 0 ? (double)RT / (double)nsteps : 1.0;
+  p->sink.want_dtde = want_dtde;
+  p->sink.delivered = false;
   if (int r = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate)) { cudaStreamSynchronize(p->copy_stream); return r; }
   p->have_transit = true;
   p->transit_grad = grad != 0;
   p->have_dtde = false;
-  if (want_dtde) {
+  if (p->sink.delivered) {  // dtdelements and the output copies ran slice by slice on the copy stream (deliver_slice)
+    CK(cudaEventRecord(p->copy_done, p->copy_stream));
+    CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
+    p->have_dtde = want_dtde;
+  } else if (want_dtde) {
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
     CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * M * 8)));
     dtdelements_kernel<<<(unsigned)nsys, 256, M * M * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
                                                                      p->bcount.as<int32_t>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), n, p->ld, RT,
-                                                                     (int)C);
+                                                                     (int)C, 0);
     p->launches++;
     p->have_dtde = true;
   }
@@ -1466,8 +1534,14 @@ int32_t nbg_transit_timing(nbg_plan* p, const double* x0, const double* v0, cons
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
   if (int r = nbg_set_pair(p, pair)) return r;
   if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
-  if (int r = nbg_transit_timing_resident(p, h, tmax, ti, ntt_body, mode, grad, jac_init)) return r;
-  if (int r = nbg_transit_fetch(p, tt, count, dtdq0, dtdelements)) return r;
+  // the host destinations are known before the run: let the last chunk stream its outputs slice by slice (OutSink)
+  const bool sliced = grad && p->out_slices > 1 && p->nsys >= p->out_slice_min && p->kmask == 0u && p->n <= NBG_RX_MAX_BODIES && !p->force_generic_jac;
+  p->sink = nbg_plan::OutSink{tt, dtdq0, dtdelements, sliced ? p->out_slices : 0, false, false};
+  const int rr = nbg_transit_timing_resident(p, h, tmax, ti, ntt_body, mode, grad, jac_init);
+  const bool delivered = p->sink.delivered;
+  p->sink = nbg_plan::OutSink{};
+  if (rr) return rr;
+  if (int r = nbg_transit_fetch(p, delivered ? nullptr : tt, count, delivered ? nullptr : dtdq0, delivered ? nullptr : dtdelements)) return r;
   return nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, t, status);
 }
 

@@ -111,7 +111,7 @@ def test_resume_equals_single_run(nb, elements):
     assert np.array_equal(a.jac_step, b.jac_step) and np.array_equal(a.jac_error, b.jac_error)
 
 
-@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
 def test_nbody_sweep(nb, oracle, n):
     # cfg 4 at test size: star + (n-1) planets m=3e-5, P_k = 1.5*1.6^(k-1), nested hierarchy, h=0.05, 40 steps, grad
     el = np.zeros((n, 7)); el[0, 0] = 1.0
@@ -140,10 +140,10 @@ def _cmp_tt(tt_gpu, count_gpu, r):
     assert np.max(np.abs(tt_gpu[mask] - r["tt"][mask]) / np.abs(r["tt"][mask])) < TOL
 
 
-@pytest.mark.parametrize("n", [10, 12, 13])
+@pytest.mark.parametrize("n", [10, 12, 14, 15])
 def test_transit_timing_above_8_bodies(nb, oracle, n):
-    # transit detection, Newton refinement and dtdq0 / dtdelements on the cfg 4 systems with more than 8 bodies: n <= 12 runs
-    # the register-resident Jacobian kernel (with queued transit steps), n = 13 the shared-memory one
+    # transit detection, Newton refinement and dtdq0 / dtdelements on the cfg 4 systems with more than 8 bodies: n <= 14 runs
+    # the register-resident Jacobian kernel (with queued transit steps), n = 15 the shared-memory one
     el = np.zeros((n, 7)); el[0, 0] = 1.0
     for k in range(1, n):
         el[k] = [3e-5, 1.5 * 1.6 ** (k - 1), 0.1 * k, 0.01, 0.0, np.pi / 2, 0.0]
@@ -351,6 +351,44 @@ def test_small_event_chunks(nb, oracle, elements):
     nb.Integrator(0.05, 6.0)(a, ta)
     nb.Integrator(0.05, 6.0, stream_budget=1)(b, tb)
     assert np.array_equal(ta.tt, tb.tt) and np.array_equal(ta.dtdq0, tb.dtdq0) and np.array_equal(a.jac_step, b.jac_step)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_one_shot_call_streams_outputs_in_slices(nb, elements, monkeypatch, mode):
+    # nbg_transit_timing (host buffers in, host buffers out) launches the last chunk's Jacobian kernel in slices of the batch and
+    # copies each finished slice out while the next one computes; results must be bit-identical to the resident call + fetch
+    import ctypes as C
+    from nbgrad import _lib
+    from nbgrad._lib import check, ptr
+    L = _lib.lib()
+    B, n, t0, h, tmax = 200, 8, 7257.0, 0.06, 6.0
+    rng = np.random.default_rng(11)
+    elb = np.broadcast_to(elements, (B, n, 7)).copy()
+    elb[1:, 1:, 1] *= 1 + 1e-4 * rng.standard_normal((B - 1, n - 1))
+    x, v, jac = nb.init_nbody_elements(elb, t0)
+    m = np.ascontiguousarray(elb[:, :, 0])
+    ji = np.ascontiguousarray(jac.transpose(0, 2, 1))
+    ntt = np.full(n, 7, dtype=np.int32); ntt[0] = 0
+    RT, M, Cn = int(ntt.sum()), 7 * n, (3 if mode else 1)
+    out = {}
+    for tag, slices in (("sliced", "3"), ("whole", "1")):
+        monkeypatch.setenv("NBG_OUT_SLICES", slices)
+        monkeypatch.setenv("NBG_OUT_SLICE_MIN", "1")
+        plan = C.c_void_p()
+        check(L.nbg_plan_create(C.byref(plan), C.c_int32(n), C.c_int64(B), C.c_int32(0), C.c_int64(0)))
+        tt, cnt = np.full((B, RT, Cn), -1.0), np.zeros((B, n), dtype=np.int64)
+        d, e = np.full((B, RT, M, Cn), -1.0), np.full((B, RT, M, Cn), -1.0)
+        xo, vo, js = np.zeros((B, n, 3)), np.zeros((B, n, 3)), np.zeros((B, M, M))
+        check(L.nbg_transit_timing(plan, ptr(x), ptr(v), ptr(m), None, C.c_double(t0), C.c_double(h), C.c_double(tmax), C.c_int32(0), ptr(ntt),
+                                   C.c_int32(mode), C.c_int32(1), ptr(ji), ptr(tt), ptr(cnt), ptr(d), ptr(e), ptr(xo), ptr(vo), None, None, ptr(js),
+                                   None, None, None, None))
+        L.nbg_plan_destroy(plan)
+        out[tag] = (tt, cnt, d, e, xo, vo, js)
+    for a, b in zip(out["sliced"], out["whole"]):
+        assert np.array_equal(a, b)
+    tt, cnt, d, e = out["sliced"][:4]
+    assert cnt.sum() > 5 * B and not np.any(tt == -1.0) and not np.any(d == -1.0) and not np.any(e == -1.0)
+    assert np.all(np.any(d != 0.0, axis=(1, 2, 3))) and np.all(np.any(e != 0.0, axis=(1, 2, 3)))
 
 
 def test_full_size_batch_65536(nb, oracle, elements):

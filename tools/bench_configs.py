@@ -4,7 +4,7 @@ measures configs[1]; these are the parity-test configurations, timed for the rec
 
   cfg 3  outer solar system, N = 5, grad = false, h = 25 d, batch 16,384  -> system-steps/s, max |dE/E|, max |dL/L|
   cfg 4  N = 2..16, nested star + planets, h = 0.05 d, grad = true, (intr)(s, N) plain driver -> system-steps/s and
-         canonical F_grad(N) TFLOP/s; for N = 9..12 also with NBG_FORCE_GENERIC_JAC=1 (shared-memory Jacobian kernel)
+         canonical F_grad(N) TFLOP/s; with --generic, N = 9..14 also with NBG_FORCE_GENERIC_JAC=1 (shared-memory Jacobian kernel)
 
 One JSON object per line on stdout.  Times are the device time of the call (CUDA events inside the library,
 nbg_last_timings[4]); inputs are resident in HBM.
@@ -72,7 +72,7 @@ def run_cfg4(L, n, nsys, steps, peak, generic=False, variant=None):
     L.nbg_plan_destroy(plan)
     rate = nsys * steps / (best[4] * 1e-3)
     tf = rate * f_grad(n) / 1e12
-    return {"config": "cfg4", "nbody": n, "variant": variant, "batch": nsys, "steps": steps, "jacobian_kernel": "shared-memory (generic)" if (generic or n > 12) else "register-resident",
+    return {"config": "cfg4", "nbody": n, "variant": variant, "batch": nsys, "steps": steps, "jacobian_kernel": "shared-memory (generic)" if (generic or n > 14) else "register-resident",
             "device_ms": float(best[4]), "system_steps_per_s": rate, "canonical_tflops": tf, "frac_fp64_peak": tf / peak if peak else None,
             "kernel_ms": {"traj": float(best[0]), "jac": float(best[2]), "phi_dense": float(best[5]), "pair_op": float(best[6])},
             "nonfinite": int((status & 1 != 0).sum())}
@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--nmin", type=int, default=2)
     ap.add_argument("--nmax", type=int, default=16)
     ap.add_argument("--skip-cfg3", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="N = 9..14: also time the shared-memory Jacobian kernel (NBG_FORCE_GENERIC_JAC=1)")
     args = ap.parse_args()
     from nbgrad import _lib
     L = _lib.lib()
@@ -124,10 +125,8 @@ def main():
         nsys = 65536 if n <= 8 else (32768 if n <= 12 else 16384)
         steps = 64 if n <= 8 else (32 if n <= 12 else 16)
         print(json.dumps(run_cfg4(L, n, nsys, steps, tfl.value)), flush=True)
-        if 9 <= n <= 12:
+        if 9 <= n <= 14 and args.generic:
             print(json.dumps(run_cfg4(L, n, nsys, steps, tfl.value, generic=True)), flush=True)
-        if n == 10:
-            print(json.dumps(run_cfg4(L, n, nsys, steps, tfl.value, variant=22)), flush=True)
 
 
 if __name__ == "__main__":
