@@ -168,6 +168,7 @@ def main():
                     help="what crosses PCIe on the way in: orbital elements (init_nbody on the device) or x, v, m + host-computed jac_init")
     ap.add_argument("--e2e-output", choices=["arrays", "chi2"], default="arrays",
                     help="with --e2e-input elements: copy out tt/dtdq0/dtdelements, or only the fused chi^2 and its gradients")
+    ap.add_argument("--stream-budget-gb", type=float, default=0.0, help="HBM for the operator streams of a chunk (0 = the library default, 1/4 of free memory)")
     ap.add_argument("--e2e-slices", type=int, default=1, help="slices (plans + host threads) of the end-to-end arm")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -195,7 +196,7 @@ def main():
     RT, M = int(ntt.sum()), 7 * NBODY
 
     plan = C.c_void_p()
-    _lib.check(L.nbg_plan_create(C.byref(plan), C.c_int32(NBODY), C.c_int64(nsys), C.c_int32(local), C.c_int64(0)))
+    _lib.check(L.nbg_plan_create(C.byref(plan), C.c_int32(NBODY), C.c_int64(nsys), C.c_int32(local), C.c_int64(int(args.stream_budget_gb * 1e9))))
     stream = torch.cuda.ExternalStream(L.nbg_cuda_stream(plan), device=torch.device("cuda", local))
     ptr = _lib.ptr
 
@@ -260,7 +261,8 @@ def main():
         for lo, hi in bounds:
             ns = hi - lo
             pl = C.c_void_p()
-            _lib.check(L.nbg_plan_create(C.byref(pl), C.c_int32(NBODY), C.c_int64(ns), C.c_int32(local), C.c_int64(int(free_b // (5 * K)))))
+            _lib.check(L.nbg_plan_create(C.byref(pl), C.c_int32(NBODY), C.c_int64(ns), C.c_int32(local),
+                                         C.c_int64(int(args.stream_budget_gb * 1e9 / K) if args.stream_budget_gb > 0 else (0 if K == 1 else int(free_b // (5 * K))))))
             bufs = dict(x=pin(x[lo:hi])[1], v=pin(v[lo:hi])[1], m=pin(m[lo:hi])[1], j=pin(jac_init[lo:hi].transpose(0, 2, 1))[1],
                         el=pin(elb[lo:hi].transpose(0, 2, 1))[1], tobs=pin(np.full(RT, T0 + 1.0))[1], sig=pin(np.full(RT, 1e-3))[1],
                         chi2=pin(np.zeros(ns))[1], gq=pin(np.zeros((ns, M)))[1], ge=pin(np.zeros((ns, M)))[1],

@@ -19,9 +19,10 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "../../include/nbgrad.h"
-#include "nbg_jacobian_rx.cuh"
+#include "nbg_jacobian_mma.cuh"
 #include "nbg_ics.cuh"
 
 using namespace nbg;
@@ -439,6 +440,147 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
   }
 }
 
+// DMMA Jacobian kernel (nbg_jacobian_mma.cuh): one block per system, mma_warps(N) warps, two 8-column tiles per warp; the same
+// work-item loop, operator staging and transit handling as jac_rx_kernel.  No fast-kick pairs (those run jac_rx_kernel<KICK>).
+template <int N, int MB>
+__global__ void __launch_bounds__(mma_warps(N) * 32, MB)
+    jac_mma_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
+                   int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
+                   long nsys, long sys0) {
+  extern __shared__ __align__(16) double smrx[];
+  constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + PF) + 12 * N * N /* stream */, SB = 2 * P * KF + 12 * N * N /* staged */,
+                G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = mma_warps(N) * 32;
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long sys = sys0 + (long)blockIdx.x;
+  if (sys >= nsys) return;
+  const MmaLane L = mma_lane(lane, warp, N);
+  const bool val[2] = {L.c[0] < M && L.t < 3, L.c[1] < M && L.t < 3};
+  MmaState<N> S;
+#pragma unroll
+  for (int T = 0; T < 2; ++T)
+#pragma unroll
+    for (int b = 0; b < N; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const size_t q = ((size_t)sys * 6 * N + 6 * b + 3 * e + L.t) * M + L.c[T];
+        S.jv[T][b][e] = val[T] ? Jv_g[q] : 0.0;
+        S.je[T][b][e] = val[T] ? Je_g[q] : 0.0;
+      }
+  double* const buf0 = smrx;
+  double* const buf1 = smrx + SB;
+  const size_t ntiles = ld / TILE;
+  rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+  double* const bk = Jbak + (size_t)sys * 8 * N * NT + tid;
+  const size_t cap = Q.cap;
+  int s = 0, ev_i = 0;
+  int32_t slot = -1;
+  uint32_t pend = 0;
+  bool in_event = false;
+  while (in_event || s < nsteps) {
+    double* const cur = (s & 1) ? buf1 : buf0;
+    double h2;
+    if (!in_event) {
+      pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
+      __pipeline_wait_prior(0);
+      __syncthreads();  // step s operators visible; everyone is done with the other buffer
+      if (s + 1 < nsteps)
+        rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+      h2 = 0.5 * h;
+    } else {
+      __syncthreads();  // everyone is done with cur
+      rx_fetch(cur, Q.stream + tile_offset(SFS, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE), G0, GSKIP, G1, tid, NT);
+      // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
+#pragma unroll
+      for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            bk[(size_t)((T * N + b) * 2 + e) * NT] = S.jv[T][b][e];
+            bk[(size_t)(4 * N + (T * N + b) * 2 + e) * NT] = S.je[T][b][e];
+          }
+      __pipeline_wait_prior(0);
+      __syncthreads();
+      h2 = 0.5 * Q.hdr[7 * cap + slot];
+    }
+    mma_step<N>(S, cur, h2, L);
+    if (in_event) {
+      // dtbvdq! (timing.jl:155-194): lane t = 0 holds rows x0, v0 and lane t = 1 rows x1, v1 of occultor ev_i minus transited body ti
+      const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
+      const double gdinv = Q.hdr[4 * cap + slot];
+      const size_t rec = (size_t)sys * O.RT + O.off[ev_i] + Q.k[slot];
+#pragma unroll
+      for (int T = 0; T < 2; ++T) {
+        double jx = 0.0, jw = 0.0;
+#pragma unroll
+        for (int b = 0; b < N; ++b) {
+          const double sg = (b == ev_i ? 1.0 : 0.0) - (b == ti ? 1.0 : 0.0);
+          jx = fma(sg, S.jv[T][b][0], jx);
+          jw = fma(sg, S.jv[T][b][1], jw);
+        }
+        const double px = L.t == 0 ? jx * dvx : (L.t == 1 ? jx * dvy : 0.0);   // (jx0 dvx, jx1 dvy)
+        const double pv = L.t == 0 ? jw * dx : (L.t == 1 ? jw * dy : 0.0);     // (jv0 dx,  jv1 dy)
+        const double a = px + __shfl_xor_sync(FULL, px, 1), bq = pv + __shfl_xor_sync(FULL, pv, 1);
+        const double dtdq = -(a + bq) * gdinv;
+        if (O.C == 1) {
+          if (val[T] && L.t == 0) O.dtdq0[rec * M + L.c[T]] = dtdq;
+        } else {
+          const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
+          const double qv = L.t == 0 ? jw * dvx : (L.t == 1 ? jw * dvy : 0.0);  // (jv0 dvx, jv1 dvy)
+          const double qx = L.t == 0 ? jx * dx : (L.t == 1 ? jx * dy : 0.0);    // (jx0 dx,  jx1 dy)
+          const double s2 = qv + __shfl_xor_sync(FULL, qv, 1), s3 = qx + __shfl_xor_sync(FULL, qx, 1);
+          if (val[T] && L.t == 0) {
+            O.dtdq0[(rec * M + L.c[T]) * 3] = dtdq;
+            O.dtdq0[(rec * M + L.c[T]) * 3 + 1] = s2 * vskyinv + dvdt * dtdq;
+            O.dtdq0[(rec * M + L.c[T]) * 3 + 2] = 2.0 * s3;
+          }
+        }
+      }
+#pragma unroll
+      for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int b = 0; b < N; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            S.jv[T][b][e] = bk[(size_t)((T * N + b) * 2 + e) * NT];
+            S.je[T][b][e] = bk[(size_t)(4 * N + (T * N + b) * 2 + e) * NT];
+          }
+    }
+    // next work item: remaining queued transits of step s, else step s + 1
+    in_event = pend != 0u;
+    if (in_event) {
+      ev_i = __ffs(pend) - 1;
+      pend &= pend - 1u;
+      slot = evlist[((size_t)s * N + ev_i) * ld + sys];
+    } else {
+      ++s;
+    }
+  }
+#pragma unroll
+  for (int T = 0; T < 2; ++T)
+    if (val[T]) {
+#pragma unroll
+      for (int b = 0; b < N; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const size_t q = ((size_t)sys * 6 * N + 6 * b + 3 * e + L.t) * M + L.c[T];
+          Jv_g[q] = S.jv[T][b][e];
+          Je_g[q] = S.je[T][b][e];
+        }
+    }
+}
+
+template <int N, int MB>
+int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
+                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, long sys0) {
+  constexpr int P = N * (N - 1) / 2, SB = 2 * P * KF + 12 * N * N;
+  const size_t smem = (size_t)2 * SB * 8;
+  if (cudaFuncSetAttribute(jac_mma_kernel<N, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(jac_mma_kernel<N, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  jac_mma_kernel<N, MB><<<(unsigned)(nsys - sys0), mma_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, nsys, sys0);
+  return 0;
+}
+
 // Split path, second stage: the Kepler operator records of the main steps.  One thread per (system, step, pair section);
 // the 32 lanes of a warp are the systems of one tile, so the section index (hence drift_first) is uniform in a warp and
 // every load/store is a 1 KB run.  Reads the SCF scalars the trajectory kernel left, runs compute_jacobian_gamma!
@@ -543,10 +685,10 @@ int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* 
 __global__ void dtdelements_kernel(const double* __restrict__ dtdq0, const double* __restrict__ jac_init, double* __restrict__ out,
                                    const int32_t* __restrict__ count, const int32_t* ntt_body, const int32_t* off, int n, size_t ld, int RT, int C,
                                    long sys0) {
-  extern __shared__ double ji[];  // M x M column-major: ji[col*M + row]
-  const int M = 7 * n;
+  extern __shared__ double ji[];  // M x M column-major with the column stride padded to an odd MP: ji[col*MP + row] (thread = col: no bank conflicts)
+  const int M = 7 * n, MP = M | 1;
   const long sys = sys0 + blockIdx.x;
-  for (int q = threadIdx.x; q < M * M; q += blockDim.x) ji[q] = jac_init[(size_t)sys * M * M + q];
+  for (int q = threadIdx.x; q < M * M; q += blockDim.x) ji[(q / M) * MP + (q % M)] = jac_init[(size_t)sys * M * M + q];
   __syncthreads();
   for (int i = 0; i < n; ++i) {
     const int nk = min(count[i * ld + sys], ntt_body[i]);
@@ -554,7 +696,7 @@ __global__ void dtdelements_kernel(const double* __restrict__ dtdq0, const doubl
       const int comp = idx % C, col = (idx / C) % M, k = idx / (C * M);
       const size_t rec = (size_t)sys * RT + off[i] + k;
       double acc = 0.0;
-      for (int row = 0; row < M; ++row) acc += dtdq0[(rec * M + row) * C + comp] * ji[col * M + row];
+      for (int row = 0; row < M; ++row) acc += dtdq0[(rec * M + row) * C + comp] * ji[col * MP + row];
       out[(rec * M + col) * C + comp] = acc;
     }
   }
@@ -712,6 +854,7 @@ struct nbg_plan {
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
+  bool jac_mma = false;  // NBG_JAC_MMA=1: DMMA Jacobian kernel (nbg_jacobian_mma.cuh) for N = 8
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
@@ -728,7 +871,9 @@ struct nbg_plan {
   int out_slices = 4;        // NBG_OUT_SLICES (<= 1: copy everything after the last kernel)
   long out_slice_min = 4096; // NBG_OUT_SLICE_MIN: smallest batch that is sliced
   std::vector<cudaEvent_t> ev_slice;   // one per slice, created on first use
+  bool trace = false;                  // NBG_TRACE=1: host wall-clock of the stages of the one-shot calls on stderr
 };
+static double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 namespace {
 
@@ -795,18 +940,11 @@ double check_step(double t0, double tmax) {  // Integrator.jl:249-259
   return -1 * sg(tmax);
 }
 
-// systems [lo, hi) are final: dtdelements for them, then their rows of tt / dtdq0 / dtdelements go to the host, all on the copy
-// stream (ordered after the jac_init upload that runs there), concurrently with the next slice's Jacobian kernel
+// systems [lo, hi) are final (their Jacobian slice and their dtdelements ran on the main stream before ev_slice[k]): their rows of
+// tt / dtdq0 / dtdelements go to the host on the copy stream, concurrently with the next slice's kernels
 int deliver_slice(nbg_plan* p, int k, long lo, long hi) {
   const size_t M = 7 * (size_t)p->n, C = p->C, RT = p->RT, cnt = (size_t)(hi - lo);
   CK(cudaStreamWaitEvent(p->copy_stream, p->ev_slice[k], 0));
-  if (p->sink.want_dtde) {
-    CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * M * 8)));
-    dtdelements_kernel<<<(unsigned)cnt, 256, M * M * 8, p->copy_stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
-                                                                           p->bcount.as<int32_t>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->n, p->ld,
-                                                                           (int)RT, (int)C, lo);
-    p->launches++;
-  }
   const size_t t0 = (size_t)lo * RT * C, q0 = t0 * M;
   if (p->sink.tt) CK(cudaMemcpyAsync(p->sink.tt + t0, p->btt.as<double>() + t0, cnt * RT * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
   if (p->sink.dtdq0) CK(cudaMemcpyAsync(p->sink.dtdq0 + q0, p->bdtdq0.as<double>() + q0, cnt * RT * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
@@ -838,6 +976,11 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   } else {
     S = std::min<long>(nsteps, 256);
   }
+  if (grad) {
+    // equal chunks: 64 steps under a budget of 9 run as 8 x 8, not 7 x 9 + 1 (a one-step chunk pays a full Jacobian load/store)
+    const long nchunks = (nsteps + S - 1) / S;
+    S = (nsteps + nchunks - 1) / nchunks;
+  }
   EventQueue Q{};
   TransitOut O{};
   int32_t* evlist = nullptr;
@@ -863,7 +1006,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     evmask = p->bevmask.as<uint32_t>();
   }
   if (grad && detect) {
-    const size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
+    const size_t per_sys = std::max<size_t>(std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32), (size_t)8 * n * mma_warps(n) * 32);
     if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
   const bool use_rx = n <= NBG_RX_MAX_BODIES && (!p->force_generic_jac || kicks);
@@ -971,6 +1114,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         int rc = 0;
         // last chunk of a call whose host outputs are known (p->sink): slices of the batch, each followed by its output copies
         const int K = (p->sink.slices > 1 && detect && !kicks && done + s == nsteps) ? p->sink.slices : 1;
+        bool waited_jinit = false;
         if (kicks) rc = launch_jac_rx_kicked(n, p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, p->kmask);
         else for (int k = 0; k < K && !rc; ++k) {
           const long lo = (nsys / TILE) * k / K * TILE, hi = k + 1 == K ? nsys : (nsys / TILE) * (k + 1) / K * TILE;
@@ -992,6 +1136,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             case 13: rc = launch_jac_rx<13, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
             case 14: rc = launch_jac_rx<14, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
             default:
+              if (p->jac_mma) { rc = launch_jac_mma<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
               // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
               if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
               else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
@@ -1011,6 +1156,15 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
               cudaEvent_t e;
               CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
               p->ev_slice.push_back(e);
+            }
+            if (p->sink.want_dtde) {  // dtdelements of the slice right behind its Jacobian kernel (jac_init: uploaded on the copy stream)
+              const size_t M = 7 * (size_t)n;
+              if (!waited_jinit) { CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0)); waited_jinit = true; }
+              CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * (M | 1) * 8)));
+              dtdelements_kernel<<<(unsigned)(hi - lo), 256, M * (M | 1) * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(),
+                                                                                        p->bdtde.as<double>(), p->bcount.as<int32_t>(),
+                                                                                        p->bntt.as<int32_t>(), p->boff.as<int32_t>(), n, ld, p->RT, p->C, lo);
+              p->launches++;
             }
             CK(cudaEventRecord(p->ev_slice[k], p->stream));
           }
@@ -1102,9 +1256,11 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   p->stream_budget = stream_budget_bytes;
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
+  if (const char* e = getenv("NBG_JAC_MMA")) p->jac_mma = (e[0] == '1');
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
   if (const char* e = getenv("NBG_OVERLAP")) p->overlap = (e[0] != '0');   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
+  if (const char* e = getenv("NBG_TRACE")) p->trace = (e[0] == '1');
   if (const char* e = getenv("NBG_OUT_SLICES")) p->out_slices = std::max(1, std::min(64, atoi(e)));
   if (const char* e = getenv("NBG_OUT_SLICE_MIN")) p->out_slice_min = std::max(1L, atol(e));
   if (alloc_state(p)) return fail(NBG_ERR_NOMEM, "state allocation failed");
@@ -1456,6 +1612,7 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   double rate = nsteps > 0 ? (double)RT / (double)nsteps : 1.0;
   p->sink.want_dtde = want_dtde;
   p->sink.delivered = false;
+  const double wr0 = wall_ms();
   if (int r = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate)) { cudaStreamSynchronize(p->copy_stream); return r; }
   p->have_transit = true;
   p->transit_grad = grad != 0;
@@ -1466,16 +1623,19 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
     p->have_dtde = want_dtde;
   } else if (want_dtde) {
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
-    CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * M * 8)));
-    dtdelements_kernel<<<(unsigned)nsys, 256, M * M * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
+    CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * (M | 1) * 8)));
+    dtdelements_kernel<<<(unsigned)nsys, 256, M * (M | 1) * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
                                                                      p->bcount.as<int32_t>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), n, p->ld, RT,
                                                                      (int)C, 0);
     p->launches++;
     p->have_dtde = true;
   }
   cudaEventRecord(e1, p->stream);
+  const double wr1 = wall_ms();
   CK(cudaStreamSynchronize(p->stream));
+  const double wr2 = wall_ms();
   finish_timings(p, tm, ev);
+  if (p->trace) fprintf(stderr, "[nbg trace] resident: launches issued in %.2f ms, then waited %.2f ms, timing readback %.2f ms\n", wr1 - wr0, wr2 - wr1, wall_ms() - wr2);
   CK(cudaGetLastError());
   return NBG_OK;
 }
@@ -1532,8 +1692,10 @@ int32_t nbg_transit_timing(nbg_plan* p, const double* x0, const double* v0, cons
                            double* dtdq0, double* dtdelements, double* x, double* v, double* xerror, double* verror, double* jac_step,
                            double* jac_error, double* dqdt, double* t, uint32_t* status) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  const double w0 = wall_ms();
   if (int r = nbg_set_pair(p, pair)) return r;
   if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
+  const double w1 = wall_ms();
   // the host destinations are known before the run: let the last chunk stream its outputs slice by slice (OutSink)
   const bool sliced = grad && p->out_slices > 1 && p->nsys >= p->out_slice_min && p->kmask == 0u && p->n <= NBG_RX_MAX_BODIES && !p->force_generic_jac;
   p->sink = nbg_plan::OutSink{tt, dtdq0, dtdelements, sliced ? p->out_slices : 0, false, false};
@@ -1541,8 +1703,14 @@ int32_t nbg_transit_timing(nbg_plan* p, const double* x0, const double* v0, cons
   const bool delivered = p->sink.delivered;
   p->sink = nbg_plan::OutSink{};
   if (rr) return rr;
+  const double w2 = wall_ms();
   if (int r = nbg_transit_fetch(p, delivered ? nullptr : tt, count, delivered ? nullptr : dtdq0, delivered ? nullptr : dtdelements)) return r;
-  return nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, t, status);
+  const double w3 = wall_ms();
+  const int rg = nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, t, status);
+  if (p->trace)
+    fprintf(stderr, "[nbg trace] transit_timing: set_state %.2f ms, resident %.2f ms (device total %.2f), fetch %.2f ms, get_state %.2f ms\n", w1 - w0,
+            w2 - w1, p->timings[4], w3 - w2, wall_ms() - w3);
+  return rg;
 }
 
 int32_t nbg_counters(nbg_plan* p, int64_t* c8) {
