@@ -442,22 +442,22 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
 
 // DMMA Jacobian kernel (nbg_jacobian_mma.cuh): one block per system, mma_warps(N) warps, two 8-column tiles per warp; the same
 // work-item loop, operator staging and transit handling as jac_rx_kernel.  No fast-kick pairs (those run jac_rx_kernel<KICK>).
-template <int N, int MB>
-__global__ void __launch_bounds__(mma_warps(N) * 32, MB)
+template <int N, int MB, int TPW>
+__global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
     jac_mma_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
                    int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
                    long nsys, long sys0) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + PF) + 12 * N * N /* stream */, SB = 2 * P * KF + 12 * N * N /* staged */,
-                G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = mma_warps(N) * 32;
+                G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = mma_warps(N, TPW) * 32;
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long sys = sys0 + (long)blockIdx.x;
   if (sys >= nsys) return;
-  const MmaLane L = mma_lane(lane, warp, N);
-  const bool val[2] = {L.c[0] < M && L.t < 3, L.c[1] < M && L.t < 3};
-  MmaState<N> S;
+  const MmaLane L = mma_lane(lane, warp, N, TPW);
+  const bool val[2] = {L.c[0] < M && L.t < 3, TPW > 1 && L.c[1] < M && L.t < 3};
+  MmaState<N, TPW> S;
 #pragma unroll
-  for (int T = 0; T < 2; ++T)
+  for (int T = 0; T < TPW; ++T)
 #pragma unroll
     for (int b = 0; b < N; ++b)
 #pragma unroll
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(mma_warps(N) * 32, MB)
   double* const buf1 = smrx + SB;
   const size_t ntiles = ld / TILE;
   rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
-  double* const bk = Jbak + (size_t)sys * 8 * N * NT + tid;
+  double* const bk = Jbak + (size_t)sys * 4 * TPW * N * NT + tid;
   const size_t cap = Q.cap;
   int s = 0, ev_i = 0;
   int32_t slot = -1;
@@ -491,26 +491,26 @@ __global__ void __launch_bounds__(mma_warps(N) * 32, MB)
       rx_fetch(cur, Q.stream + tile_offset(SFS, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE), G0, GSKIP, G1, tid, NT);
       // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
 #pragma unroll
-      for (int T = 0; T < 2; ++T)
+      for (int T = 0; T < TPW; ++T)
 #pragma unroll
         for (int b = 0; b < N; ++b)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             bk[(size_t)((T * N + b) * 2 + e) * NT] = S.jv[T][b][e];
-            bk[(size_t)(4 * N + (T * N + b) * 2 + e) * NT] = S.je[T][b][e];
+            bk[(size_t)(2 * TPW * N + (T * N + b) * 2 + e) * NT] = S.je[T][b][e];
           }
       __pipeline_wait_prior(0);
       __syncthreads();
       h2 = 0.5 * Q.hdr[7 * cap + slot];
     }
-    mma_step<N>(S, cur, h2, L);
+    mma_step<N, TPW>(S, cur, h2, L);
     if (in_event) {
       // dtbvdq! (timing.jl:155-194): lane t = 0 holds rows x0, v0 and lane t = 1 rows x1, v1 of occultor ev_i minus transited body ti
       const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
       const double gdinv = Q.hdr[4 * cap + slot];
       const size_t rec = (size_t)sys * O.RT + O.off[ev_i] + Q.k[slot];
 #pragma unroll
-      for (int T = 0; T < 2; ++T) {
+      for (int T = 0; T < TPW; ++T) {
         double jx = 0.0, jw = 0.0;
 #pragma unroll
         for (int b = 0; b < N; ++b) {
@@ -537,13 +537,13 @@ __global__ void __launch_bounds__(mma_warps(N) * 32, MB)
         }
       }
 #pragma unroll
-      for (int T = 0; T < 2; ++T)
+      for (int T = 0; T < TPW; ++T)
 #pragma unroll
         for (int b = 0; b < N; ++b)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             S.jv[T][b][e] = bk[(size_t)((T * N + b) * 2 + e) * NT];
-            S.je[T][b][e] = bk[(size_t)(4 * N + (T * N + b) * 2 + e) * NT];
+            S.je[T][b][e] = bk[(size_t)(2 * TPW * N + (T * N + b) * 2 + e) * NT];
           }
     }
     // next work item: remaining queued transits of step s, else step s + 1
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(mma_warps(N) * 32, MB)
     }
   }
 #pragma unroll
-  for (int T = 0; T < 2; ++T)
+  for (int T = 0; T < TPW; ++T)
     if (val[T]) {
 #pragma unroll
       for (int b = 0; b < N; ++b)
@@ -570,14 +570,14 @@ __global__ void __launch_bounds__(mma_warps(N) * 32, MB)
     }
 }
 
-template <int N, int MB>
+template <int N, int MB, int TPW>
 int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
                    const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, long sys0) {
   constexpr int P = N * (N - 1) / 2, SB = 2 * P * KF + 12 * N * N;
   const size_t smem = (size_t)2 * SB * 8;
-  if (cudaFuncSetAttribute(jac_mma_kernel<N, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  cudaFuncSetAttribute(jac_mma_kernel<N, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_mma_kernel<N, MB><<<(unsigned)(nsys - sys0), mma_warps(N) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, nsys, sys0);
+  if (cudaFuncSetAttribute(jac_mma_kernel<N, MB, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(jac_mma_kernel<N, MB, TPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  jac_mma_kernel<N, MB, TPW><<<(unsigned)(nsys - sys0), mma_warps(N, TPW) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, nsys, sys0);
   return 0;
 }
 
@@ -854,7 +854,7 @@ struct nbg_plan {
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
-  bool jac_mma = false;  // NBG_JAC_MMA=1: DMMA Jacobian kernel (nbg_jacobian_mma.cuh) for N = 8
+  int jac_mma = 0;  // NBG_JAC_MMA: DMMA Jacobian kernel (nbg_jacobian_mma.cuh) for N = 8, measured 12-18 % slower than jac_rx_kernel; 1: two tiles per warp, 2: one
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
@@ -868,7 +868,7 @@ struct nbg_plan {
   // dtdelements and its device-to-host copies on the copy stream while the next slice computes.
   struct OutSink { double* tt = nullptr; double* dtdq0 = nullptr; double* dtde = nullptr; int slices = 0; bool want_dtde = false, delivered = false; };
   OutSink sink;
-  int out_slices = 4;        // NBG_OUT_SLICES (<= 1: copy everything after the last kernel)
+  int out_slices = 8;        // NBG_OUT_SLICES (<= 1: copy everything after the last kernel)
   long out_slice_min = 4096; // NBG_OUT_SLICE_MIN: smallest batch that is sliced
   std::vector<cudaEvent_t> ev_slice;   // one per slice, created on first use
   bool trace = false;                  // NBG_TRACE=1: host wall-clock of the stages of the one-shot calls on stderr
@@ -1006,7 +1006,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     evmask = p->bevmask.as<uint32_t>();
   }
   if (grad && detect) {
-    const size_t per_sys = std::max<size_t>(std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32), (size_t)8 * n * mma_warps(n) * 32);
+    const size_t per_sys = std::max<size_t>(std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32), (size_t)8 * n * std::max(mma_warps(n, 2) * 2, mma_warps(n, 1)) * 16);
     if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
   const bool use_rx = n <= NBG_RX_MAX_BODIES && (!p->force_generic_jac || kicks);
@@ -1136,7 +1136,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             case 13: rc = launch_jac_rx<13, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
             case 14: rc = launch_jac_rx<14, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
             default:
-              if (p->jac_mma) { rc = launch_jac_mma<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
+              if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
+              if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
               // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
               if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
               else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
@@ -1256,7 +1257,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   p->stream_budget = stream_budget_bytes;
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
-  if (const char* e = getenv("NBG_JAC_MMA")) p->jac_mma = (e[0] == '1');
+  if (const char* e = getenv("NBG_JAC_MMA")) p->jac_mma = atoi(e);
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
   if (const char* e = getenv("NBG_OVERLAP")) p->overlap = (e[0] != '0');   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));

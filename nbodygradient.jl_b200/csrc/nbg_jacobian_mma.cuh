@@ -19,21 +19,27 @@
 // sit in one lane).  The dense phisalpha operator is applied the same way: A = x components of body d, B = the weights of two
 // output bodies interleaved (even n -> body 2 bp, odd n -> body 2 bp + 1), so C again lands in the owning lane.
 // Replaces the same reference code as nbg_jacobian_rx.cuh (ahl21.jl:5-95 Jacobian half, timing.jl:155-194).
+//
+// STATUS: experiment, off by default (NBG_JAC_MMA=1: two tiles per warp, 250 registers; =2: one tile per warp, 128 registers, 14
+// warps per SM).  Parity-green at 1e-11 on the N = 8 tests (r01l), but SLOWER than jac_rx_kernel on B200: 798 ms / 757 ms against
+// 675 ms per 3 bench steps.  ncu (profiles/r01l_jac_mma_kernel.txt): the top stall is the fixed-latency wait behind each DMMA, the
+// FP64 pipe is the only busy unit (shared-memory pipe 18 %), i.e. the padded product (4 DMMA = 32 DFMA-equivalents per pair and warp
+// against 18 DFMA per thread) costs more pipe time than the operand delivery it saves.  Kept as measured evidence for DESIGN.md 4.
 #pragma once
 #include "nbg_jacobian_rx.cuh"
 
 namespace nbg {
 
 __host__ __device__ constexpr int mma_tiles(int n) { return (7 * n + 7) / 8; }
-__host__ __device__ constexpr int mma_warps(int n) { return (mma_tiles(n) + 1) / 2; }
+__host__ __device__ constexpr int mma_warps(int n, int tpw = 2) { return (mma_tiles(n) + tpw - 1) / tpw; }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int N> struct MmaState {
-  double jv[2][N][2];  // [tile][body][0: x_t, 1: v_t]
-  double je[2][N][2];
+template <int N, int TPW> struct MmaState {  // TPW: 8-column tiles per warp (2: fewer operand loads per column; 1: twice the warps per SM)
+  double jv[TPW][N][2];  // [tile][body][0: x_t, 1: v_t]
+  double je[TPW][N][2];
 };
 
 struct MmaLane {
@@ -46,13 +52,13 @@ struct MmaLane {
   bool odd;        // g & 1
 };
 
-__device__ __forceinline__ MmaLane mma_lane(int lane, int warp, int n) {
+__device__ __forceinline__ MmaLane mma_lane(int lane, int warp, int n, int tpw) {
   MmaLane L;
   L.g = lane >> 2; L.t = lane & 3;
   const int M = 7 * n;
 #pragma unroll
   for (int T = 0; T < 2; ++T) {
-    L.c[T] = (2 * warp + T) * 8 + L.g;
+    L.c[T] = (tpw * warp + (T < tpw ? T : 0)) * 8 + L.g;
     L.dm[T] = (L.c[T] < M && L.c[T] % 7 == 6) ? L.c[T] / 7 : -1;
   }
   L.odd = (L.g & 1) != 0;
@@ -65,14 +71,14 @@ __device__ __forceinline__ MmaLane mma_lane(int lane, int warp, int n) {
 }
 
 // pair update between bodies PA < PB (comp_sum_matrix! of jac_ij * rows(i,j), ahl21.jl:31-35, 64-68)
-template <int N, int PA, int PB>
-__device__ __forceinline__ void mma_pair(MmaState<N>& S, const double* __restrict__ R, const MmaLane& L) {
+template <int N, int TPW, int PA, int PB>
+__device__ __forceinline__ void mma_pair(MmaState<N, TPW>& S, const double* __restrict__ R, const MmaLane& L) {
   const double b0 = L.bvalid ? R[L.koff0] : 0.0;
   const double b1 = L.bvalid ? R[L.koff1] : 0.0;
   const double2 mm = *reinterpret_cast<const double2*>(R + KF_MI);
   constexpr int ci = 7 * PA + 6, cj = 7 * PB + 6;
 #pragma unroll
-  for (int T = 0; T < 2; ++T) {
+  for (int T = 0; T < TPW; ++T) {
     const double d0 = S.jv[T][PA][0] - S.jv[T][PB][0];
     const double d1 = S.jv[T][PA][1] - S.jv[T][PB][1];
     double w0 = 0.0, w1 = 0.0;
@@ -101,39 +107,41 @@ __device__ __forceinline__ void mma_pair(MmaState<N>& S, const double* __restric
 }
 
 // drift_grad! (ahl21.jl:318-331): x rows += h/2 * v rows, Kahan; lane-local in this layout
-template <int N> __device__ __forceinline__ void mma_drift(MmaState<N>& S, double h2) {
+template <int N, int TPW> __device__ __forceinline__ void mma_drift(MmaState<N, TPW>& S, double h2) {
 #pragma unroll
-  for (int T = 0; T < 2; ++T)
+  for (int T = 0; T < TPW; ++T)
 #pragma unroll
     for (int b = 0; b < N; ++b) ksum(S.jv[T][b][0], S.je[T][b][0], h2 * S.jv[T][b][1]);
 }
 // comp_sum_matrix! with a zero addend (jac_kick = 0, ahl21.jl:23,93): folds jac_error into jac_step
-template <int N> __device__ __forceinline__ void mma_fold(MmaState<N>& S) {
+template <int N, int TPW> __device__ __forceinline__ void mma_fold(MmaState<N, TPW>& S) {
 #pragma unroll
-  for (int T = 0; T < 2; ++T)
+  for (int T = 0; T < TPW; ++T)
 #pragma unroll
     for (int b = 0; b < N; ++b) { ksum_m(S.jv[T][b][0], S.je[T][b][0], 0.0); ksum_m(S.jv[T][b][1], S.je[T][b][1], 0.0); }
 }
 
 // jac_step (+)= jac_phi * jac_step with the dense operator W (layout of phi_dense_fields) in shared memory
-template <int N> __device__ __forceinline__ void mma_phisalpha(MmaState<N>& S, const double* __restrict__ W, const MmaLane& L) {
+template <int N, int TPW> __device__ __forceinline__ void mma_phisalpha(MmaState<N, TPW>& S, const double* __restrict__ W, const MmaLane& L) {
   constexpr int NP = (N + 1) / 2;
-  double dv[2][2 * NP];  // [tile][body]: this lane's component t of the v-row increment
+  double dv[TPW][2 * NP];  // [tile][body]: this lane's component t of the v-row increment
   static_for<0, NP>([&](auto BPc) {
     constexpr int bp = decltype(BPc)::value;
     const bool valid = L.bvalid && (2 * bp + 1 < N || !L.odd);
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    double c[TPW][2];
+#pragma unroll
+    for (int T = 0; T < TPW; ++T) { c[T][0] = 0.0; c[T][1] = 0.0; }
     static_for<0, N>([&](auto Dc) {
       constexpr int d = decltype(Dc)::value;
       const double bw = valid ? W[L.woff + (6 * bp * N + d) * 4] : 0.0;
-      dmma884(c00, c01, S.jv[0][d][0], bw);
-      dmma884(c10, c11, S.jv[1][d][0], bw);
+#pragma unroll
+      for (int T = 0; T < TPW; ++T) dmma884(c[T][0], c[T][1], S.jv[T][d][0], bw);
     });
-    dv[0][2 * bp] = c00; dv[0][2 * bp + 1] = c01;
-    dv[1][2 * bp] = c10; dv[1][2 * bp + 1] = c11;
+#pragma unroll
+    for (int T = 0; T < TPW; ++T) { dv[T][2 * bp] = c[T][0]; dv[T][2 * bp + 1] = c[T][1]; }
   });
 #pragma unroll
-  for (int T = 0; T < 2; ++T)
+  for (int T = 0; T < TPW; ++T)
 #pragma unroll
     for (int b = 0; b < N; ++b) {
       double a = dv[T][b];
@@ -145,19 +153,19 @@ template <int N> __device__ __forceinline__ void mma_phisalpha(MmaState<N>& S, c
 }
 
 // one AHL21 Jacobian step (no fast-kick pairs) from a staged operator block [2P Kepler records | dense phisalpha operator]
-template <int N> __device__ __forceinline__ void mma_step(MmaState<N>& S, const double* __restrict__ blk, double h2, const MmaLane& L) {
+template <int N, int TPW> __device__ __forceinline__ void mma_step(MmaState<N, TPW>& S, const double* __restrict__ blk, double h2, const MmaLane& L) {
   constexpr int P = N * (N - 1) / 2;
   using SW = RxSweep<N, N, false>;  // full unroll: positions are bodies, no rotation
   auto rotate = [&](auto Kc) { static_assert(decltype(Kc)::value % N == 0, "full unroll never rotates"); };
-  auto pair = [&](auto PA, auto PB, const double* R, int, int) { mma_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, L); };
-  mma_drift<N>(S, h2);
-  mma_fold<N>(S);
+  auto pair = [&](auto PA, auto PB, const double* R, int, int) { mma_pair<N, TPW, decltype(PA)::value, decltype(PB)::value>(S, R, L); };
+  mma_drift<N, TPW>(S, h2);
+  mma_fold<N, TPW>(S);
   SW::asc(rotate, blk, KF, pair);
-  mma_phisalpha<N>(S, blk + 2 * P * KF, L);
+  mma_phisalpha<N, TPW>(S, blk + 2 * P * KF, L);
   rotate(std::integral_constant<int, SW::KTOP * N - SW::A1>{});
   SW::desc(rotate, blk + P * KF, KF, pair);
-  mma_drift<N>(S, h2);
-  mma_fold<N>(S);
+  mma_drift<N, TPW>(S, h2);
+  mma_fold<N, TPW>(S);
 }
 
 }  // namespace nbg
