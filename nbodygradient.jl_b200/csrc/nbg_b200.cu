@@ -176,8 +176,8 @@ __device__ __noinline__ double transit_pre_iteration(const Body& b0, int n, doub
 
 // ------------------------------------------------------------------------------------------------------------------
 // findtransit! (timing.jl:31-110).  One thread per queued transit.
-template <bool GRAD, bool KICKS = false>
-__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask, int npre) {
+template <bool GRAD, bool KICKS = false, int MB = 1>  // MB: blocks per SM the register allocation is capped for (NBG_TRANSIT_MB)
+__global__ void __launch_bounds__(128, MB) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask, int npre) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(*Q.n, Q.cap);
   if (e >= nq) return;
@@ -630,11 +630,46 @@ __global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(doubl
   else if constexpr (N <= 8)  // fast-kick pairs exist for N <= 8 only (pair mask in 32 bits)
     phi_dense_rows_kicked<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y, phi_rec_offset(N, blockIdx.z), phi_dense_offset(N, true, blockIdx.z));
 }
+// the same (no fast-kick pairs) with the per-pair tensors cached in shared memory (phi_dense_rows_cached): FULL for N <= 10
+// (one block per SM at N = 8), the T / gam cache alone for N = 11, 12 (207 KB at N = 12)
+template <int N, bool FULL>
+__global__ void __launch_bounds__(32 * N, FULL ? 1 : 512 / (32 * N)) phi_dense_cached_kernel(double* __restrict__ base, size_t ntiles, long nitems,
+                                                                                           const int32_t* __restrict__ nitems_dev) {
+  extern __shared__ double sm_phi[];
+  const long idx = (long)blockIdx.x * 32 + threadIdx.x;
+  const long nv = nitems_dev ? min((long)*nitems_dev, nitems) : nitems;
+  if ((long)blockIdx.x * 32 >= nv) return;  // uniform: the whole tile is empty
+  double* blk = base + tile_offset(step_fields(N, false), ntiles, blockIdx.y, (size_t)idx);
+  phi_dense_rows_cached<N, FULL>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y, idx < nv, sm_phi,
+                                 sm_phi + (size_t)(N * (N - 1) / 2) * phi_tgf(FULL) * 32, (int)threadIdx.x);
+}
+template <int N, bool FULL> int launch_phi_dense_cached(cudaStream_t st, const dim3& grid, const dim3& block, double* base, size_t ntiles, long nitems,
+                                                        const int32_t* nitems_dev) {
+  const size_t smem = phi_cache_bytes(N, FULL);
+  if (cudaFuncSetAttribute(phi_dense_cached_kernel<N, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  phi_dense_cached_kernel<N, FULL><<<grid, block, smem, st>>>(base, ntiles, nitems, nitems_dev);
+  return 0;
+}
 // main steps: ntiles = ld / 32, nsteps steps; queued transits: ntiles = 0 (one "step"), nitems_dev = device count of queued transits
-int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long nitems, const int32_t* nitems_dev, int nsteps, bool kicked = false) {
+int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long nitems, const int32_t* nitems_dev, int nsteps, bool kicked = false,
+                     int cached = 2) {
   if (nitems <= 0 || nsteps <= 0) return 0;
   const dim3 grid((unsigned)((nitems + 31) / 32), (unsigned)nsteps, kicked ? 3u : 1u), block(32, n);
   const int kf = kicked ? 1 : 0;
+  if (!kicked && cached) switch (n) {
+    case 2: return cached == 2 ? launch_phi_dense_cached<2, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<2, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 3: return cached == 2 ? launch_phi_dense_cached<3, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<3, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 4: return cached == 2 ? launch_phi_dense_cached<4, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<4, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 5: return cached == 2 ? launch_phi_dense_cached<5, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<5, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 6: return cached == 2 ? launch_phi_dense_cached<6, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<6, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 7: return cached == 2 ? launch_phi_dense_cached<7, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<7, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 8: return cached == 2 ? launch_phi_dense_cached<8, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<8, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 9: return cached == 2 ? launch_phi_dense_cached<9, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<9, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 10: return cached == 2 ? launch_phi_dense_cached<10, true>(st, grid, block, base, ntiles, nitems, nitems_dev) : launch_phi_dense_cached<10, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 11: return launch_phi_dense_cached<11, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    case 12: return launch_phi_dense_cached<12, false>(st, grid, block, base, ntiles, nitems, nitems_dev);
+    default: break;  // 13, 14: the cache does not fit in shared memory
+  }
   switch (n) {
     case 2: phi_dense_kernel<2><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 3: phi_dense_kernel<3><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
@@ -844,16 +879,19 @@ struct nbg_plan {
   cudaStream_t copy_stream = nullptr;  // uploads that overlap the stepping (jac_init)
   cudaEvent_t copy_done = nullptr;
   cudaStream_t aux_stream = nullptr;   // operator kernels of the main steps, concurrent with the transit refinement
-  cudaEvent_t ev_traj = nullptr, ev_ops = nullptr;
+  cudaEvent_t ev_traj = nullptr, ev_ops = nullptr, ev_ops2 = nullptr;
+  cudaStream_t aux2_stream = nullptr;  // NBG_OVERLAP=2: the dense phisalpha operators on a third stream
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
   DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters, belem;
   DevBuf stage[8];  // staging for host<->device conversions
-  bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true;
+  bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true, overlap3 = false;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
+  int phi_cached = 2;  // NBG_PHI_CACHED: 0 = phi_dense_kernel without the shared-memory cache of the per-pair tensors, 1 = T / gam cached, 2 = all pair fields
+  int transit_mb = 1;  // NBG_TRANSIT_MB: 3 / 4 = transit_kernel capped at 168 / 128 registers (more resident warps, more spills)
   int jac_mma = 0;  // NBG_JAC_MMA: DMMA Jacobian kernel (nbg_jacobian_mma.cuh) for N = 8, measured 12-18 % slower than jac_rx_kernel; 1: two tiles per warp, 2: one
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
@@ -1078,17 +1116,23 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       tm.end();
       p->launches++;
     }
+    const bool fork3 = fork && p->overlap3;
     if (grad && use_rx) {
-      tm.begin(5, aux);
-      if (launch_phi_dense(aux, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      cudaStream_t aux2 = fork3 ? p->aux2_stream : aux;
+      if (fork3) CK(cudaStreamWaitEvent(p->aux2_stream, p->ev_traj, 0));
+      tm.begin(5, aux2);
+      if (launch_phi_dense(aux2, n, p->bstream.as<double>(), ld / TILE, nsys, nullptr, s, kicks, p->phi_cached)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
       tm.end();
       p->launches++;
+      if (fork3) CK(cudaEventRecord(p->ev_ops2, aux2));
     }
     if (fork) CK(cudaEventRecord(p->ev_ops, aux));
     if (detect) {
       tm.begin(1);
       const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
       if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+      else if (grad && p->transit_mb == 3) transit_kernel<true, false, 3><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+      else if (grad && p->transit_mb == 4) transit_kernel<true, false, 4><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
@@ -1096,12 +1140,13 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       p->launches++;
       if (grad && use_rx) {
         tm.begin(5);
-        if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1, kicks)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+        if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1, kicks, p->phi_cached)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
         tm.end();
         p->launches++;
       }
     }
     if (fork) CK(cudaStreamWaitEvent(p->stream, p->ev_ops, 0));
+    if (fork3 && grad && use_rx) CK(cudaStreamWaitEvent(p->stream, p->ev_ops2, 0));
     if (grad) {
       p->counters_host[6] = (unsigned long long)S;
       p->counters_host[7] += 1;
@@ -1249,6 +1294,8 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   CK(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&p->ev_traj, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&p->ev_ops, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&p->ev_ops2, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&p->aux2_stream, cudaStreamNonBlocking));
   if (stream_budget_bytes <= 0) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
@@ -1258,8 +1305,10 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
   if (const char* e = getenv("NBG_JAC_MMA")) p->jac_mma = atoi(e);
+  if (const char* e = getenv("NBG_TRANSIT_MB")) p->transit_mb = atoi(e);
+  if (const char* e = getenv("NBG_PHI_CACHED")) p->phi_cached = atoi(e);
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
-  if (const char* e = getenv("NBG_OVERLAP")) p->overlap = (e[0] != '0');   // 0: operator kernels on the main stream (clean per-kernel times)
+  if (const char* e = getenv("NBG_OVERLAP")) { p->overlap = (e[0] != '0'); p->overlap3 = (e[0] == '2'); }   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
   if (const char* e = getenv("NBG_TRACE")) p->trace = (e[0] == '1');
   if (const char* e = getenv("NBG_OUT_SLICES")) p->out_slices = std::max(1, std::min(64, atoi(e)));
@@ -1277,6 +1326,7 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   if (p->aux_stream) cudaStreamSynchronize(p->aux_stream);
+  if (p->aux2_stream) cudaStreamSynchronize(p->aux2_stream);
   DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
                    &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
                    &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters, &p->belem};
@@ -1286,6 +1336,8 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->copy_done) cudaEventDestroy(p->copy_done);
   if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+  if (p->aux2_stream) cudaStreamDestroy(p->aux2_stream);
+  if (p->ev_ops2) cudaEventDestroy(p->ev_ops2);
   if (p->ev_traj) cudaEventDestroy(p->ev_traj);
   if (p->ev_ops) cudaEventDestroy(p->ev_ops);
   for (cudaEvent_t e : p->ev_slice) cudaEventDestroy(e);

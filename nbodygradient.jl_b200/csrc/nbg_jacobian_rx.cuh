@@ -250,6 +250,146 @@ template <int N> __device__ __forceinline__ void phi_dense_rows(double* __restri
   }
 }
 
+// phi_dense_rows with the per-pair tensors cached in shared memory.  In phi_dense_rows a thread rebuilds T and gam of a pair from the
+// record 15 times per column block d (120 times per step: ~40 % of its FP64 instructions and most of its L1 traffic, 97 KB per
+// system-step for 5.4 KB of records).  Here the block (32 systems x N bodies) first builds them once per pair, then the per-body sums
+// A_dd = - sum_l m_l T_dl, and the row loop reads both from shared memory (lane = system: conflict-free).  Same arithmetic in the same
+// order as phi_dense_rows: results are bit-identical.
+//   tg[(p * TGF + q) * 32 + lane]: q < 6: T, 6..8: gam oriented from the lower-index body, 9: its mass, 10: the other mass
+//   dg[(d * 7 + q) * 32 + lane]:   q < 6: A_dd, 6: m_d
+// FULL: fields 11..16 also cache r_ij (3), fac1, r^2 and us of the pair, so that the row loop reads nothing but shared memory except
+// the F / dF/dr terms of the 2 column blocks d = i, j (N <= 10: 214 KB at N = 10)
+__host__ __device__ constexpr int phi_tgf(bool full) { return full ? 17 : 11; }
+__host__ __device__ constexpr size_t phi_cache_bytes(int n, bool full) { return (size_t)(n * (n - 1) / 2 * phi_tgf(full) + n * 7) * 32 * 8; }
+
+template <int N, bool FULL>
+__device__ __forceinline__ void phi_dense_rows_cached(double* __restrict__ blk, size_t stride, size_t idx, int i, bool live, double* __restrict__ tg,
+                                                       double* __restrict__ dg, int lane) {
+  constexpr int P = N * (N - 1) / 2, TGF = phi_tgf(FULL);
+  const double* __restrict__ PH = blk + ((size_t)(2 * P * KF / 4) * stride + idx) * 4;  // group 0 of record 0
+  double* __restrict__ OUT = blk + ((size_t)(P * (2 * KF + PF) / 4) * stride + idx) * 4;
+  const size_t gs = stride * 4;  // doubles between consecutive groups of one system
+  auto grp = [&](int p, int g) { return reinterpret_cast<const double2*>(PH + (size_t)(p * (PF / 4) + g) * gs); };
+  // phase 1: T, gam, masses of every pair, once
+  for (int p = i; p < P; p += N) {
+    const double2 u = __ldg(grp(p, 0)), v = __ldg(grp(p, 0) + 1), e = __ldg(grp(p, 1)), f = __ldg(grp(p, 1) + 1);
+    const double r0 = u.x, r1 = u.y, r2 = v.x, g3 = v.y, g5 = e.x;
+    double* o = tg + (size_t)p * TGF * 32 + lane;
+    o[0 * 32] = g3 - g5 * r0 * r0; o[1 * 32] = -g5 * r0 * r1; o[2 * 32] = -g5 * r0 * r2;
+    o[3 * 32] = g3 - g5 * r1 * r1; o[4 * 32] = -g5 * r1 * r2; o[5 * 32] = g3 - g5 * r2 * r2;
+    o[6 * 32] = g3 * r0; o[7 * 32] = g3 * r1; o[8 * 32] = g3 * r2;
+    o[9 * 32] = e.y; o[10 * 32] = f.x;
+    if (FULL) {
+      const double2 g = __ldg(grp(p, 2));
+      o[11 * 32] = r0; o[12 * 32] = r1; o[13 * 32] = r2; o[14 * 32] = f.y; o[15 * 32] = g.x; o[16 * 32] = g.y;
+    }
+  }
+  __syncthreads();
+  {  // A_dd and m_d of body d = i
+    const int d = i;
+    double diag[6] = {0, 0, 0, 0, 0, 0}, md = 0.0;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      if (l == d) continue;
+      const double* t = tg + (size_t)rx_pair_index(N, d < l ? d : l, d < l ? l : d) * TGF * 32 + lane;
+      md = t[(d < l ? 9 : 10) * 32];
+      const double ml = t[(d < l ? 10 : 9) * 32];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) diag[q] = fma(-ml, t[q * 32], diag[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) dg[(d * 7 + q) * 32 + lane] = diag[q];
+    dg[(d * 7 + 6) * 32 + lane] = md;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int d = 0; d < N; ++d) {
+    double diag[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) diag[q] = dg[(d * 7 + q) * 32 + lane];
+    const double md = dg[(d * 7 + 6) * 32 + lane];
+    // A[b][d]: x part (6) and mass part (3)
+    auto Aget = [&](int b, double (&ax)[6], double (&am)[3]) {
+      if (b == d) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ax[q] = diag[q];
+        am[0] = 0.0; am[1] = 0.0; am[2] = 0.0;
+      } else {
+        const double* t = tg + (size_t)rx_pair_index(N, d < b ? d : b, d < b ? b : d) * TGF * 32 + lane;
+        const double sg = d < b ? 1.0 : -1.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ax[q] = md * t[q * 32];
+        am[0] = sg * t[6 * 32]; am[1] = sg * t[7 * 32]; am[2] = sg * t[8 * 32];
+      }
+    };
+    double axi[6], ami[3];
+    Aget(i, axi, ami);
+    double acc[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[k][q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const int p = rx_pair_index(N, i < j ? i : j, i < j ? j : i);
+      double r[3], mj, fac1, rsq, us;
+      if (FULL) {
+        const double* t = tg + (size_t)p * TGF * 32 + lane;
+        r[0] = t[11 * 32]; r[1] = t[12 * 32]; r[2] = t[13 * 32];
+        mj = t[(i < j ? 10 : 9) * 32]; fac1 = t[14 * 32]; rsq = t[15 * 32]; us = t[16 * 32];
+      } else {
+        const double2 a = __ldg(grp(p, 0)), b = __ldg(grp(p, 0) + 1), e = __ldg(grp(p, 1)), f = __ldg(grp(p, 1) + 1), g = __ldg(grp(p, 2));
+        r[0] = a.x; r[1] = a.y; r[2] = b.x;
+        mj = i < j ? f.x : e.y; fac1 = f.y; rsq = g.x; us = g.y;
+      }
+      const double sg = i < j ? 1.0 : -1.0;
+      double axj[6], amj[3];
+      Aget(j, axj, amj);
+      double u[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) u[q] = axi[q] - axj[q];
+      const double col[4][3] = {{u[0], u[1], u[2]}, {u[1], u[3], u[4]}, {u[2], u[4], u[5]}, {ami[0] - amj[0], ami[1] - amj[1], ami[2] - amj[2]}};
+      double ev[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double ru = 3.0 * (r[0] * col[q][0] + r[1] * col[q][1] + r[2] * col[q][2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ev[q][k] = fac1 * (r[k] * ru - rsq * col[q][k]);
+      }
+      if (d == i || d == j) {
+        const double2 g1 = __ldg(grp(p, 2) + 1), h0 = __ldg(grp(p, 3)), h1 = __ldg(grp(p, 3) + 1), k0 = __ldg(grp(p, 4)), k1 = __ldg(grp(p, 4) + 1),
+                      l0 = __ldg(grp(p, 5));
+        const double F[3] = {g1.x, g1.y, h0.x};
+        const double Rm[9] = {h0.y, h1.x, h1.y, k0.x, k0.y, k1.x, k1.y, l0.x, l0.y};
+        const double sr = d == i ? 1.0 : -1.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) ev[q][k] = fma(sr, Rm[3 * k + q], ev[q][k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ev[3][k] = fma(sg * us, r[k], ev[3][k]);
+        if (d == j) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc[k][3] = fma(sg, F[k], acc[k][3]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k][q] = fma(mj, ev[q][k], acc[k][q]);
+    }
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double2* o = reinterpret_cast<double2*>(OUT + (size_t)((3 * i + k) * N + d) * gs);
+        o[0] = make_double2(acc[k][0], acc[k][1]);
+        o[1] = make_double2(acc[k][2], acc[k][3]);
+      }
+    }
+  }
+}
+
 // The same expansion with fast-kick pairs (nbg_kicks.cuh): records carry a class (the accelerations a^c only sum pairs of the
 // same class) and a direct-kick coefficient kappa.  rec_off / out_off: field offsets of the record set and of its dense block.
 template <int N> __device__ __forceinline__ void phi_dense_rows_kicked(double* __restrict__ blk, size_t stride, size_t idx, int i, size_t rec_off,

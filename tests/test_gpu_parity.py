@@ -353,6 +353,33 @@ def test_small_event_chunks(nb, oracle, elements):
     assert np.array_equal(ta.tt, tb.tt) and np.array_equal(ta.dtdq0, tb.dtdq0) and np.array_equal(a.jac_step, b.jac_step)
 
 
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_dmma_jacobian_kernel_variant(nb, oracle, elements, monkeypatch, variant):
+    # the experimental FP64 tensor-core Jacobian kernel (NBG_JAC_MMA, nbg_jacobian_mma.cuh; off by default because it is slower)
+    # must stay correct: transit timing on a perturbed TRAPPIST-1 batch against the oracle, and against the default kernel
+    monkeypatch.setenv("NBG_JAC_MMA", variant)
+    nb.release_plans()
+    B, n, t0, h, tmax = 3, 8, 7257.0, 0.06, 12.0
+    rng = np.random.default_rng(8 + int(variant))
+    elb = np.broadcast_to(elements, (B, n, 7)).copy()
+    elb[1:, 1:, 1] *= 1 + 1e-4 * rng.standard_normal((B - 1, n - 1))
+    ic = nb.ElementsIC(t0, n, elb)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s, tt)
+    nb.release_plans()
+    monkeypatch.delenv("NBG_JAC_MMA")
+    s0, tt0 = nb.State(ic), nb.TransitTiming(tmax, ic)
+    nb.Integrator(h, tmax)(s0, tt0)
+    nb.release_plans()
+    assert np.array_equal(tt.tt, tt0.tt) and np.array_equal(s.x, s0.x)      # the trajectory does not depend on the Jacobian kernel
+    assert rel(tt.dtdq0, tt0.dtdq0) < 1e-12 and rel(s.jac_step, s0.jac_step) < 1e-12
+    for b in range(B):
+        so, r = _tt_oracle(oracle, elb[b], t0, h, tmax, tt.ntt)
+        _cmp_tt(tt.tt[b], tt.count[b], r)
+        assert rel(tt.dtdq0[b], r["dtdq0"]) < TOL and rel(tt.dtdelements[b], r["dtdelements"]) < TOL
+        assert rel(s.jac_step[b], so["jac_step_cm"].T) < TOL
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_one_shot_call_streams_outputs_in_slices(nb, elements, monkeypatch, mode):
     # nbg_transit_timing (host buffers in, host buffers out) launches the last chunk's Jacobian kernel in slices of the batch and
