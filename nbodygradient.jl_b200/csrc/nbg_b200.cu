@@ -176,8 +176,9 @@ __device__ __noinline__ double transit_pre_iteration(const Body& b0, int n, doub
 
 // ------------------------------------------------------------------------------------------------------------------
 // findtransit! (timing.jl:31-110).  One thread per queued transit.
-template <bool GRAD, bool KICKS = false, int MB = 1>  // MB: blocks per SM the register allocation is capped for (NBG_TRANSIT_MB)
-__global__ void __launch_bounds__(128, MB) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask, int npre) {
+// (capping the registers for 3 / 4 blocks per SM was measured: 167 -> 198 / 206 ms per 3 bench steps, the spills cost more than the warps hide)
+template <bool GRAD, bool KICKS = false>
+__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask, int npre) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(*Q.n, Q.cap);
   if (e >= nq) return;
@@ -891,7 +892,6 @@ struct nbg_plan {
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
   int phi_cached = 2;  // NBG_PHI_CACHED: 0 = phi_dense_kernel without the shared-memory cache of the per-pair tensors, 1 = T / gam cached, 2 = all pair fields
-  int transit_mb = 1;  // NBG_TRANSIT_MB: 3 / 4 = transit_kernel capped at 168 / 128 registers (more resident warps, more spills)
   int jac_mma = 0;  // NBG_JAC_MMA: DMMA Jacobian kernel (nbg_jacobian_mma.cuh) for N = 8, measured 12-18 % slower than jac_rx_kernel; 1: two tiles per warp, 2: one
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
@@ -1131,8 +1131,6 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       tm.begin(1);
       const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
       if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
-      else if (grad && p->transit_mb == 3) transit_kernel<true, false, 3><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
-      else if (grad && p->transit_mb == 4) transit_kernel<true, false, 4><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
       else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
@@ -1183,15 +1181,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             default:
               if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
               if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
-              // tuning variants (NBG_RX_UNROLL: 1, 2, 4 = pivots per block; +10: no per-group barrier; +20: 2 blocks/SM, 255 registers)
-              if (p->rx_unroll == 4) rc = launch_jac_rx<8, 4>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 1) rc = launch_jac_rx<8, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 12) rc = launch_jac_rx<8, 2, false>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 14) rc = launch_jac_rx<8, 4, false>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 22) rc = launch_jac_rx<8, 2, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 32) rc = launch_jac_rx<8, 2, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 18) rc = launch_jac_rx<8, 8, false, 3>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 34) rc = launch_jac_rx<8, 4, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+              // NBG_RX_UNROLL: 38 (default) = full unroll, no per-group barrier, 2 blocks/SM at 255 registers; 22 = pivot blocks of 2 with a barrier per
+              // group; 48 = two systems per block in lockstep; anything else = pivot blocks of 2 at 3 blocks/SM.  (The other combinations of
+              // pivots per block / barrier / blocks per SM were measured in r01c-r01h and removed: DESIGN.md 5, "measured and rejected".)
+              if (p->rx_unroll == 22) rc = launch_jac_rx<8, 2, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
               else if (p->rx_unroll == 48) rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
               else if (p->rx_unroll == 38) rc = launch_jac_rx<8, 8, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
               else rc = launch_jac_rx<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
@@ -1305,7 +1298,6 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_FORCE_GENERIC_JAC")) p->force_generic_jac = (e[0] == '1');
   if (const char* e = getenv("NBG_RX_UNROLL")) p->rx_unroll = atoi(e);
   if (const char* e = getenv("NBG_JAC_MMA")) p->jac_mma = atoi(e);
-  if (const char* e = getenv("NBG_TRANSIT_MB")) p->transit_mb = atoi(e);
   if (const char* e = getenv("NBG_PHI_CACHED")) p->phi_cached = atoi(e);
   if (const char* e = getenv("NBG_SPLIT_TRAJ")) p->split_traj = (e[0] != '0');
   if (const char* e = getenv("NBG_OVERLAP")) { p->overlap = (e[0] != '0'); p->overlap3 = (e[0] == '2'); }   // 0: operator kernels on the main stream (clean per-kernel times)
