@@ -318,7 +318,8 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * main_steps / (float(t2.item()) * 1e-3), "unit": "system-steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "slices": K, "input": args.e2e_input, "output": args.e2e_output if args.e2e_input == "elements" else "arrays", "transits_checked": int(sum(B["c"].sum() for _, B in slices)), "chi2_sum": float(sum(B["chi2"].sum() for _, B in slices)),
-               "timing": "host wall clock around %d blocking nbg_transit_timing calls per slice, max over ranks" % args.steps}
+               "timing": "host wall clock around %d blocking nbg_transit_timing calls per slice, max over ranks" % args.steps,
+               "output_streaming": "the last chunk's Jacobian kernel runs in %s batch slices, each copied out while the next computes" % os.environ.get("NBG_OUT_SLICES", "8")}
         for pl, _B in slices:
             L.nbg_plan_destroy(pl)
 

@@ -83,6 +83,7 @@ class State:
         self.verror = np.zeros((B, n, 3))
         self.pair = np.zeros((n, n), dtype=bool)
         self.status = np.zeros(B, dtype=np.uint32)
+        self._fresh = True   # no integrator call has touched this State yet: jac_step = I, the error terms and dq/dh are zero
 
     def _init_on_device(self, ic, device):
         L = _lib.lib()
@@ -150,6 +151,7 @@ class State:
         if with_jac:
             self.jac_step[...] = js.transpose(0, 2, 1)
             self.jac_error[...] = je.transpose(0, 2, 1)
+        self._fresh = False
 
 
 def dState(ic):
@@ -292,23 +294,42 @@ class Integrator:
         L = _lib.lib()
         plan = self._p(s)
         n, B, ntt, M = s.n, s.nsys, tt.ntt, 7 * s.n
-        resident = s._upload(plan, grad)
         ntt_body = np.full(n, ntt, dtype=np.int32)
         mode = 1 if tt.ncomp == 3 else 0
-        ji = None
         want_dtde = grad and s.jac_init.size
-        if want_dtde and not resident:   # resident: jac_init computed on the device is used (jac_init = NULL)
-            ji = np.ascontiguousarray(s.jac_init.transpose(0, 2, 1))
-        check(L.nbg_transit_timing_resident(plan, C.c_double(self.h), C.c_double(self.tmax), C.c_int32(tt.ti), ptr(ntt_body), C.c_int32(mode),
-                                            C.c_int32(1 if grad else 0), ptr(ji)))
         Cn = tt.ncomp
         shp_t = (B, n, ntt) if Cn == 1 else (B, n, ntt, 3)
         shp_d = (B, n, ntt, n, 7) if Cn == 1 else (B, n, ntt, n, 7, 3)
         t_raw = np.zeros(shp_t)
         d_raw = np.zeros(shp_d) if grad else None
         e_raw = np.zeros(shp_d) if want_dtde else None
-        check(L.nbg_transit_fetch(plan, ptr(t_raw), ptr(tt.count), ptr(d_raw), ptr(e_raw)))
-        s._download(plan, grad)
+        one_shot = (s._fresh and s._resident_plan is None and not s.xerror.any() and not s.verror.any() and not s.dqdt.any()
+                    and not s.jac_error.any())
+        if one_shot:
+            # a fresh State(ic): the one-shot entry point knows the host destinations before it starts, so the library copies the
+            # outputs out slice by slice during the last chunk instead of after the last kernel
+            pr = np.asfortranarray(s.pair.astype(np.uint8))
+            m_c = np.ascontiguousarray(s.m, dtype=np.float64)
+            ji = np.ascontiguousarray(s.jac_init.transpose(0, 2, 1)) if want_dtde else None
+            js = np.empty((B, M, M)) if grad else None
+            je = np.empty((B, M, M)) if grad else None
+            check(L.nbg_transit_timing(plan, ptr(s.x), ptr(s.v), ptr(m_c), ptr(pr) if pr.any() else None, C.c_double(float(s.t[0])),
+                                       C.c_double(self.h), C.c_double(self.tmax), C.c_int32(tt.ti), ptr(ntt_body), C.c_int32(mode),
+                                       C.c_int32(1 if grad else 0), ptr(ji), ptr(t_raw), ptr(tt.count), ptr(d_raw), ptr(e_raw), ptr(s.x), ptr(s.v),
+                                       ptr(s.xerror), ptr(s.verror), ptr(js), ptr(je), ptr(s.dqdt) if grad else None, ptr(s.t), ptr(s.status)))
+            if grad:
+                s.jac_step[...] = js.transpose(0, 2, 1)
+                s.jac_error[...] = je.transpose(0, 2, 1)
+            s._fresh = False
+        else:
+            resident = s._upload(plan, grad)
+            ji = None
+            if want_dtde and not resident:   # resident: jac_init computed on the device is used (jac_init = NULL)
+                ji = np.ascontiguousarray(s.jac_init.transpose(0, 2, 1))
+            check(L.nbg_transit_timing_resident(plan, C.c_double(self.h), C.c_double(self.tmax), C.c_int32(tt.ti), ptr(ntt_body), C.c_int32(mode),
+                                                C.c_int32(1 if grad else 0), ptr(ji)))
+            check(L.nbg_transit_fetch(plan, ptr(t_raw), ptr(tt.count), ptr(d_raw), ptr(e_raw)))
+            s._download(plan, grad)
         if Cn == 1:
             tt.tt[...] = t_raw
             if grad:
