@@ -181,10 +181,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    # rank 0 prints exactly ONE JSON line on stdout.  NCCL writes its version banner (and anything NCCL_DEBUG asks for) to the C-level
+    # stdout, so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a saved copy of the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     L = _lib.lib()
@@ -385,7 +388,8 @@ def main():
         rate, dt, r = cpu_run(ns, args.ref_window, cores, x, v, m, jac_init)
         out["cpu_baseline"] = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
                                "sample": "%d systems x %d steps (%.1f s), oracle -O3 build, one system per thread" % (ns, args.ref_window, dt)}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if plan is not None:
         L.nbg_plan_destroy(plan)
     if dist is not None:
