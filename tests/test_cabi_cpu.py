@@ -83,3 +83,16 @@ def test_host_ic_layer_matches_oracle(nb, oracle, elements):
         nb.get_default_ICs("nope")
     with pytest.raises(ValueError):
         nb.Elements(m=1.0, P=1.0, ecosw=1.2)
+
+
+def test_runtime_knobs_are_documented():
+    # every environment variable the library reads is listed in INTEGRATION.md section 6 (and nothing stale is listed)
+    src = ""
+    csrc = os.path.join(ROOT, "nbodygradient.jl_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh")):
+            src += open(os.path.join(csrc, f)).read()
+    read = set(re.findall(r'getenv\("(NBG_[A-Z0-9_]+)"\)', src))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    listed = set(re.findall(r"`(NBG_[A-Z0-9_]+)`", doc.split("## 6.")[1])) - {"NBG_JAC_MMA=1"}
+    assert read and read == listed, read ^ listed
