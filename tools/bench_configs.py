@@ -102,6 +102,7 @@ def run_cfg3(L, nsys, steps):
         E1, L1 = energy_angmom(m, xo[b], vo[b])
         dE = max(dE, abs(E1 / E0 - 1)); dL = max(dL, float(np.linalg.norm(L1 - L0) / np.linalg.norm(L0)))
     return {"config": "cfg3", "nbody": 5, "batch": nsys, "steps": steps + 256, "h": h, "grad": False, "device_ms": float(kt[4]),
+            "system0_x": xo[0].tolist(), "system0_v": vo[0].tolist(),
             "system_steps_per_s": nsys * steps / (kt[4] * 1e-3), "max_abs_dE_over_E": dE, "max_abs_dL_over_L": dL,
             "note": "energy / angular momentum after %d steps of h = 25 d, sampled over 256 systems of the batch" % (steps + 256)}
 
@@ -112,6 +113,7 @@ def main():
     ap.add_argument("--nmin", type=int, default=2)
     ap.add_argument("--nmax", type=int, default=16)
     ap.add_argument("--skip-cfg3", action="store_true")
+    ap.add_argument("--skip-cfg4", action="store_true")
     ap.add_argument("--generic", action="store_true", help="N = 9..14: also time the shared-memory Jacobian kernel (NBG_FORCE_GENERIC_JAC=1)")
     args = ap.parse_args()
     from nbgrad import _lib
@@ -121,7 +123,7 @@ def main():
     print(json.dumps({"fp64_peak_tflops_measured": tfl.value}), flush=True)
     if not args.skip_cfg3:
         print(json.dumps(run_cfg3(L, 16384, args.cfg3_steps)), flush=True)
-    for n in range(args.nmin, args.nmax + 1):
+    for n in range(args.nmin, (args.nmax if not args.skip_cfg4 else args.nmin - 1) + 1):
         nsys = 65536 if n <= 8 else (32768 if n <= 12 else 16384)
         steps = 64 if n <= 8 else (32 if n <= 12 else 16)
         print(json.dumps(run_cfg4(L, n, nsys, steps, tfl.value)), flush=True)
