@@ -16,6 +16,7 @@
 module NbodyGradientB200
 
 using NbodyGradient
+using LinearAlgebra: I
 import NbodyGradient: Integrator, State, TransitTiming, TransitParameters, TransitOutput, check_step
 
 export b200, B200Integrator, nbg_device_count
@@ -101,26 +102,37 @@ function upload(p, ss::Vector{State{Float64}}, grad::Bool)
     end
 end
 
-function download!(p, ss::Vector{State{Float64}}, grad::Bool)
-    B, n = length(ss), ss[1].n
+# host buffers for the final state of a batch (ABI layout) and their scatter back into the reference's State objects
+function state_buffers(B::Int, n::Int, grad::Bool)
     M = 7n
     x = Array{Float64}(undef, 3, n, B); v = similar(x); xe = similar(x); ve = similar(x)
     t = Vector{Float64}(undef, B); status = Vector{UInt32}(undef, B)
     js = grad ? Array{Float64}(undef, M, M, B) : nothing
     je = grad ? Array{Float64}(undef, M, M, B) : nothing
     dq = grad ? Array{Float64}(undef, M, B) : nothing
-    chk(ccall((:nbg_get_state, LIB), Int32,
-              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}),
-              p, x, v, xe, ve, grad ? js : C_NULL, grad ? je : C_NULL, grad ? dq : C_NULL, t, status))
+    return (x=x, v=v, xe=xe, ve=ve, js=js, je=je, dq=dq, t=t, status=status)
+end
+function scatter!(ss::Vector{State{Float64}}, o, grad::Bool)
     for (b, s) in enumerate(ss)
-        s.x .= @view x[:, :, b]; s.v .= @view v[:, :, b]; s.xerror .= @view xe[:, :, b]; s.verror .= @view ve[:, :, b]
-        s.t[1] = t[b]
+        s.x .= @view o.x[:, :, b]; s.v .= @view o.v[:, :, b]; s.xerror .= @view o.xe[:, :, b]; s.verror .= @view o.ve[:, :, b]
+        s.t[1] = o.t[b]
         if grad
-            s.jac_step .= @view js[:, :, b]; s.jac_error .= @view je[:, :, b]; s.dqdt .= @view dq[:, b]
+            s.jac_step .= @view o.js[:, :, b]; s.jac_error .= @view o.je[:, :, b]; s.dqdt .= @view o.dq[:, b]
         end
     end
-    return status
+    return o.status
 end
+
+function download!(p, ss::Vector{State{Float64}}, grad::Bool)
+    o = state_buffers(length(ss), ss[1].n, grad)
+    chk(ccall((:nbg_get_state, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}),
+              p, o.x, o.v, o.xe, o.ve, grad ? o.js : C_NULL, grad ? o.je : C_NULL, grad ? o.dq : C_NULL, o.t, o.status))
+    return scatter!(ss, o, grad)
+end
+
+# A State that no integrator call has touched: jac_step = I, error terms and dq/dh zero (what State(ic) constructs, Integrator.jl:82-103)
+isfresh(s::State{Float64}) = all(iszero, s.xerror) && all(iszero, s.verror) && all(iszero, s.jac_error) && all(iszero, s.dqdt) && s.jac_step == I
 
 # ---- (intr)(s, time; grad)  Integrator.jl:159-197 ----------------------------------------------------------------------
 function (bi::B200Integrator)(ss::Vector{State{Float64}}, time::Float64; grad::Bool=true)
@@ -157,7 +169,6 @@ function (bi::B200Integrator)(ss::Vector{State{Float64}}, tts::Vector{<:TransitO
     M, ntt, ti, C = 7n, tts[1].ntt, tts[1].ti, ncomp(tts[1])
     all(t -> t.ntt == ntt && t.ti == ti, tts) || throw(ArgumentError("all transit outputs of a batch must share ntt and ti"))
     p = plan(n, B, bi.device)
-    upload(p, ss, grad)
     ntt_body = fill(Int32(ntt), n)
     jinit = C_NULL
     ji = nothing
@@ -165,15 +176,32 @@ function (bi::B200Integrator)(ss::Vector{State{Float64}}, tts::Vector{<:TransitO
         ji = Array{Float64}(undef, M, M, B)
         for (b, s) in enumerate(ss); ji[:, :, b] .= s.jac_init; end
     end
-    chk(ccall((:nbg_transit_timing_resident, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Int32}, Int32, Int32, Ptr{Float64}),
-              p, bi.h, bi.tmax, ti - 1, ntt_body, C == 3 ? 1 : 0, grad, grad ? ji : jinit))
     # ABI layout (C order): tt[sys][i][k][c], dtdq0[sys][i][k][p][q][c]  ==  Julia arrays (c, k, i, b) and (c, q, p, k, i, b)
     traw = zeros(Float64, C, ntt, n, B)
     count = zeros(Int64, n, B)
     draw = grad ? zeros(Float64, C, 7, n, ntt, n, B) : nothing
     eraw = grad ? zeros(Float64, C, 7, n, ntt, n, B) : nothing
-    chk(ccall((:nbg_transit_fetch, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
-              p, traw, count, grad ? draw : C_NULL, grad ? eraw : C_NULL))
+    out = nothing
+    if all(isfresh, ss)
+        # fresh State(ic) objects: the one-shot entry point takes the host arrays for inputs AND outputs, so the library can copy the
+        # outputs out slice by slice while the last chunk still computes (INTEGRATION.md 6)
+        x, v, m, _, _ = pack(ss)
+        out = state_buffers(B, n, grad)
+        pairarg = any(ss[1].pair) ? reinterpret(UInt8, ss[1].pair) : C_NULL
+        chk(ccall((:nbg_transit_timing, LIB), Int32,
+                  (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Float64, Float64, Float64, Int32, Ptr{Int32}, Int32, Int32,
+                   Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                   Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}),
+                  p, x, v, m, pairarg, ss[1].t[1], bi.h, bi.tmax, ti - 1, ntt_body, C == 3 ? 1 : 0, grad,
+                  grad ? ji : jinit, traw, count, grad ? draw : C_NULL, grad ? eraw : C_NULL, out.x, out.v, out.xe, out.ve,
+                  grad ? out.js : C_NULL, grad ? out.je : C_NULL, grad ? out.dq : C_NULL, out.t, out.status))
+    else
+        upload(p, ss, grad)
+        chk(ccall((:nbg_transit_timing_resident, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Int32}, Int32, Int32, Ptr{Float64}),
+                  p, bi.h, bi.tmax, ti - 1, ntt_body, C == 3 ? 1 : 0, grad, grad ? ji : jinit))
+        chk(ccall((:nbg_transit_fetch, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                  p, traw, count, grad ? draw : C_NULL, grad ? eraw : C_NULL))
+    end
     for (b, tt) in enumerate(tts)
         tt.count .= @view count[:, b]
         if C == 1
@@ -190,7 +218,7 @@ function (bi::B200Integrator)(ss::Vector{State{Float64}}, tts::Vector{<:TransitO
             end
         end
     end
-    return download!(p, ss, grad)
+    return out === nothing ? download!(p, ss, grad) : scatter!(ss, out, grad)
 end
 
 # single-system forms: a batch of one
