@@ -1,6 +1,6 @@
 # Final round script: parity tests, smoke, bench (both arms), ncu launch list.  ROUND names the outputs.
 mkdir -p gpurun_out
-R=${ROUND:-r01n}
+R=${ROUND:-r02a}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
 timeout 600 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
@@ -13,6 +13,6 @@ timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 tail -3 gpurun_out/smoke.log; tail -3 gpurun_out/bench.err; cat gpurun_out/${R}_bench.json; cat gpurun_out/${R}_bench_reference.json
 python - <<'PY'
 import json, os
-d = json.load(open("gpurun_out/%s_bench_serialized.json" % os.environ.get("ROUND", "r01n")))
+d = json.load(open("gpurun_out/%s_bench_serialized.json" % os.environ.get("ROUND", "r02a")))
 print("serialized", "value %.4g" % d["value"], {k: round(v) for k, v in d["kernel_ms"].items()})
 PY
