@@ -210,3 +210,24 @@ def test_transit_parameters_vs_float128_fd(oracle, elements):
     assert isapprox_maxabs(np.arcsinh(r["dtdelements"]), np.arcsinh(num))
     # v_sky row on its own is well conditioned
     assert isapprox_maxabs(np.arcsinh(r["dtdelements"][1][mask]), np.arcsinh(num[1][mask]))
+
+
+def test_cfg3_full_length_oracle_vs_recorded_gpu_state(oracle):
+    # BASELINE cfg 3 at its full length (10^6 steps of h = 25 d, grad = false): the oracle's energy / angular-momentum drift, and the
+    # final state the CUDA path produced for the same system on a B200 (tests/golden/cfg3_full_gpu_system0.json, generated by
+    # tools/bench_configs.py) against the oracle run here.  Tolerances: 5e-11 (x) and 5e-10 (v) relative in max-norm after 10^6 steps
+    # (measured 1.8e-11 and 1.1e-10; the two paths differ in FMA contraction and libm at the 1e-16 level per step).
+    import json
+    import os
+    from golden.outer_ss import outer_ss_cartesian, energy_angmom
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cfg3_full_gpu_system0.json")))
+    m, x, v = outer_ss_cartesian()
+    s = oracle.new_state(x, v, m, 0.0)
+    oracle.integrate(s, g["h"], nsteps=g["steps"], grad=False)
+    E0, L0 = energy_angmom(m, x, v)
+    E1, L1 = energy_angmom(m, s["x"], s["v"])
+    assert abs(E1 / E0 - 1) < 2e-13 and np.linalg.norm(L1 - L0) / np.linalg.norm(L0) < 1e-14
+    assert g["gpu_max_abs_dE_over_E"] < 2e-13   # the GPU batch drifts no more than that either (recorded with the fixture)
+    xg, vg = np.array(g["x"]), np.array(g["v"])
+    assert np.max(np.abs(xg - s["x"])) / np.max(np.abs(s["x"])) < 5e-11
+    assert np.max(np.abs(vg - s["v"])) / np.max(np.abs(s["v"])) < 5e-10
