@@ -49,7 +49,8 @@ extern "C" {
 /* per-system status bits */
 #define NBG_ST_NONFINITE 1u       /* x, v not finite at the end */
 #define NBG_ST_TRANSIT_ITMAX 2u   /* findtransit! Newton hit its 20-iteration cap (timing.jl:49,70) */
-#define NBG_ST_EVENT_OVERFLOW 4u  /* more transits in one chunk than the event queue holds; some were dropped */
+#define NBG_ST_EVENT_OVERFLOW 4u  /* reserved (v1: transits dropped on queue overflow).  Never set since v2: a chunk whose transit queue
+                                     overflows is re-run with a queue of the measured size (nbg_chunk_retries counts the re-runs). */
 #define NBG_ST_NTT_OVERFLOW 8u    /* a body had more transits than its ntt capacity (counted, not stored: timing.jl:18-19) */
 
 typedef struct nbg_plan nbg_plan;
@@ -57,11 +58,21 @@ typedef struct nbg_plan nbg_plan;
 int32_t nbg_version(void);
 const char* nbg_last_error(void);
 int32_t nbg_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+int32_t nbg_build_flags(void);  /* bit 0: built with -DNBG_EXPERIMENTS (the rejected kernel variants of DESIGN.md 5 are selectable) */
 
 /* A plan holds device buffers for `nsys` systems of `nbody` bodies on CUDA device `device`.
  * stream_budget_bytes bounds the operator-stream buffer (0 = default: 1/4 of free device memory). */
 int32_t nbg_plan_create(nbg_plan** plan, int32_t nbody, int64_t nsys, int32_t device, int64_t stream_budget_bytes);
+/* One plan over several devices (systems are independent, no exchange step): the batch is cut into ndev contiguous
+ * slices, slice k lives on CUDA device devices[k] with its own child plan, stream and host thread; every call on the returned plan
+ * runs on all slices concurrently and reads / writes the slices of the caller's arrays in place (the host-side "gather" is implicit in
+ * the disjoint slices).  Results are bit-identical to a single-device plan.  A device may be listed more than once. */
+int32_t nbg_plan_create_multi(nbg_plan** plan, int32_t nbody, int64_t nsys, const int32_t* devices, int32_t ndev, int64_t stream_budget_bytes);
+int32_t nbg_plan_devices(nbg_plan* plan, int32_t* devices, int32_t cap); /* returns the number of slices, fills devices[0..min(cap, slices)) */
 int32_t nbg_plan_destroy(nbg_plan* plan);
+/* Bumped by every call that changes the resident state (set_state*, integrate*, transit*): a caller that skips an upload because
+ * "the plan already holds my state" must compare this token with the one it saw when it put the state there. */
+int64_t nbg_state_generation(nbg_plan* plan);
 
 /* ---- resident state (State{T}, Integrator.jl:49-72) ------------------------------------------------------
  * nbg_set_state uploads x, v, m (required) and optionally xerror, verror, jac_step, jac_error, dqdt
@@ -115,8 +126,14 @@ int32_t nbg_integrate(nbg_plan* plan, const double* x0, const double* v0, const 
  * mode 0 = TransitTiming; mode 1 = TransitParameters: tt/dtdq0/dtdelements get a leading component axis of 3
  * (time, v_sky, b_sky^2): ttbv[sys][off[i]+k][3], dtbvdq0[sys][off[i]+k][7*p+q][3].
  * grad = 0: times only (dtdq0/dtdelements untouched, no Jacobian propagated).
- * The *_resident form leaves outputs on the device (nbg_transit_fetch copies them out); the one-shot form uses host
- * buffers for everything. */
+ * The *_resident form keeps DENSE outputs on the device (nbg_transit_fetch copies them out, nbg_transit_chi2 reduces them); it fails
+ * with NBG_ERR_NOMEM when nsys * RT * 7N doubles do not fit.  The one-shot form nbg_transit_timing takes host buffers for everything
+ * and never holds more than one chunk of outputs on the device: after every chunk of steps the rows of the transits found in it
+ * (tt, dtdq0, dtdelements: one row per transit) go to pinned staging on a copy stream and are scattered into the caller's arrays
+ * while the next chunks compute.  That is the call for the full-length configurations (65,536 systems x 1600 d: 2 x 83 GB of
+ * gradients).  nbg_transit_fetch with only `count` non-NULL works after either form.
+ * No transit is ever dropped: the number queued in a chunk is read back after the trajectory kernel, and a queue that was too small
+ * is grown and the chunk re-run from its saved start state before anything consumed it. */
 int32_t nbg_transit_timing_resident(nbg_plan* plan, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode,
                                     int32_t grad, const double* jac_init_host_or_null);
 int32_t nbg_transit_fetch(nbg_plan* plan, double* tt, int64_t* count, double* dtdq0, double* dtdelements);
@@ -128,6 +145,16 @@ int32_t nbg_transit_fetch(nbg_plan* plan, double* tt, int64_t* count, double* dt
  * 1: [sys][RT].  Slots with sigma <= 0 or a non-finite t_obs are skipped.  grad_q0 / grad_elements may be NULL. */
 int32_t nbg_transit_chi2(nbg_plan* plan, const double* t_obs, const double* sigma, int32_t per_system, double* chi2, double* grad_q0,
                          double* grad_elements);
+/* The same run with the likelihood FUSED into the Jacobian kernel: chi2[sys] and grad[sys][7p+q] are accumulated where
+ * d tt / d q0 is produced, so no dtdq0 / dtdelements row is ever stored and 1 + M doubles per system leave the device.  Runs from the
+ * resident state (nbg_set_state / nbg_set_state_elements).  seed_jac_init = 1 (needs nbg_set_state_elements(..., want_jac_init = 1))
+ * starts jac_step from jac_init instead of the identity, which makes every derivative one with respect to the orbital elements:
+ * grad is then d chi2 / d elements (Julia dtdelements index order) and the resident jac_step afterwards is d state / d elements;
+ * seed_jac_init = 0 gives d chi2 / d q0.  grad = 0: chi2 only (no Jacobian is propagated).  count [sys][N] and tt [sys][RT] are
+ * optional outputs (NULL = not wanted); t_obs / sigma / per_system as in nbg_transit_chi2. */
+int32_t nbg_transit_chi2_fused(nbg_plan* plan, double h, double tmax, int32_t ti, const int32_t* ntt_body, const double* t_obs,
+                               const double* sigma, int32_t per_system, int32_t seed_jac_init, int32_t grad, double* chi2, double* grad_out,
+                               int64_t* count, double* tt);
 int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0,
                            double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad,
                            const double* jac_init, double* tt, int64_t* count, double* dtdq0, double* dtdelements, double* x,
@@ -141,13 +168,15 @@ int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, c
  *  at it),
  *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main + transit),
  *  c[6] steps per chunk of the last call (operator-stream budget), c[7] Jacobian-kernel launches.
+ * For a multi-device plan the counters are summed over the slices and the timings are the maximum over the slices.
  * nbg_last_timings: device milliseconds (CUDA events on the plan's stream) spent in the last compute call in the
  *  trajectory kernel [0], transit-refinement kernel [1], Jacobian kernel [2], everything else [3]; [4] = total;
  *  [5] = dense phisalpha-operator kernel; [6] = pair-operator kernel (split path); [7] reserved (0). */
 int32_t nbg_counters(nbg_plan* plan, int64_t* c8);
 int32_t nbg_counters_reset(nbg_plan* plan);
 int32_t nbg_last_timings(nbg_plan* plan, double* ms8);
-int64_t nbg_cuda_stream(nbg_plan* plan); /* cudaStream_t of the plan, for callers that time with their own events */
+int64_t nbg_cuda_stream(nbg_plan* plan); /* cudaStream_t of the plan (of its first slice), for callers that time with their own events */
+int64_t nbg_chunk_retries(nbg_plan* plan); /* chunks re-run because their transit queue was too small, since plan creation / nbg_counters_reset */
 /* FP64 (DFMA) pipe peak of `device`, measured with 8 independent FMA chains per thread: the roofline denominator
  * for this path (the driver-written MEASURED_PEAKS.json carries HBM and bf16 figures only). */
 int32_t nbg_fp64_peak(int32_t device, double* tflops, double* ms);

@@ -19,7 +19,7 @@ using NbodyGradient
 using LinearAlgebra: I
 import NbodyGradient: Integrator, State, TransitTiming, TransitParameters, TransitOutput, check_step
 
-export b200, B200Integrator, nbg_device_count
+export b200, B200Integrator, nbg_device_count, chi2_fused
 
 const LIB = get(ENV, "NBGRAD_B200_LIB", "libnbgrad_b200")
 
@@ -38,35 +38,47 @@ end
 
 nbg_device_count() = Int(ccall((:nbg_device_count, LIB), Int32, ()))
 
-# ---- plan cache: (nbody, nsys, device) -> nbg_plan* -----------------------------------------------------------------
-const PLANS = Dict{Tuple{Int,Int,Int},Ptr{Cvoid}}()
-function plan(n::Int, nsys::Int, device::Int)
-    get!(PLANS, (n, nsys, device)) do
-        p = Ref{Ptr{Cvoid}}(C_NULL)
-        chk(ccall((:nbg_plan_create, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int64, Int32, Int64), p, n, nsys, device, 0))
-        p[]
+# ---- plan cache: (nbody, nsys, devices) -> nbg_plan*; bounded (a plan keeps its device buffers), oldest entry evicted ------------
+const PLANS = Dict{Tuple{Int,Int,Vector{Int32}},Ptr{Cvoid}}()
+const PLAN_ORDER = Tuple{Int,Int,Vector{Int32}}[]
+const MAX_PLANS = 4
+function plan(n::Int, nsys::Int, devices::Vector{Int32})
+    key = (n, nsys, devices)
+    haskey(PLANS, key) && return PLANS[key]
+    while length(PLAN_ORDER) >= MAX_PLANS
+        old = popfirst!(PLAN_ORDER)
+        ccall((:nbg_plan_destroy, LIB), Int32, (Ptr{Cvoid},), pop!(PLANS, old))
     end
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    # one device: nbg_plan_create; several: one contiguous slice of the batch, one child plan and one host thread per device
+    # inside the library (nbg_plan_create_multi) -- every call below then runs on all devices concurrently
+    chk(ccall((:nbg_plan_create_multi, LIB), Int32, (Ref{Ptr{Cvoid}}, Int32, Int64, Ptr{Int32}, Int32, Int64), p, n, nsys, devices, length(devices), 0))
+    PLANS[key] = p[]
+    push!(PLAN_ORDER, key)
+    return p[]
 end
 function release_plans()
     for p in values(PLANS)
         ccall((:nbg_plan_destroy, LIB), Int32, (Ptr{Cvoid},), p)
     end
-    empty!(PLANS)
+    empty!(PLANS); empty!(PLAN_ORDER)
 end
+atexit(release_plans)
 
 """
-    b200(intr::Integrator; device=0)
+    b200(intr::Integrator; device=0, devices=[device])
 
-Wrap a reference `Integrator` so that calling it runs on the B200.  `h`, `tmax` are read ONCE, by value (the reference
-mutates `intr.h` inside `(intr)(s,N)`, Integrator.jl:218,232, so an Integrator must not be shared across threads).
+Wrap a reference `Integrator` so that calling it runs on the B200(s).  `devices = 0:7` shards a batch over the eight GPUs of a box
+(contiguous slices, no collective; SURVEY 8(e)).  `h`, `tmax` are read ONCE, by value (the reference mutates `intr.h` inside
+`(intr)(s,N)`, Integrator.jl:218,232, so an Integrator must not be shared across threads).
 """
 struct B200Integrator
     h::Float64
     t0::Float64
     tmax::Float64
-    device::Int
+    device::Vector{Int32}
 end
-b200(intr::Integrator; device::Int=0) = B200Integrator(intr.h, intr.t0, intr.tmax, device)
+b200(intr::Integrator; device::Int=0, devices=[device]) = B200Integrator(intr.h, intr.t0, intr.tmax, collect(Int32, devices))
 
 # ---- packing: Julia column-major arrays with the system index slowest are exactly the ABI layout ----------------------
 function pack(ss::Vector{State{Float64}})
@@ -183,8 +195,8 @@ function (bi::B200Integrator)(ss::Vector{State{Float64}}, tts::Vector{<:TransitO
     eraw = grad ? zeros(Float64, C, 7, n, ntt, n, B) : nothing
     out = nothing
     if all(isfresh, ss)
-        # fresh State(ic) objects: the one-shot entry point takes the host arrays for inputs AND outputs, so the library can copy the
-        # outputs out slice by slice while the last chunk still computes (INTEGRATION.md 6)
+        # fresh State(ic) objects: the one-shot entry point takes the host arrays for inputs AND outputs, so the library streams every
+        # chunk's transit rows into them while the next chunk computes and never holds the full arrays on the device (INTEGRATION.md 6)
         x, v, m, _, _ = pack(ss)
         out = state_buffers(B, n, grad)
         pairarg = any(ss[1].pair) ? reinterpret(UInt8, ss[1].pair) : C_NULL
@@ -219,6 +231,27 @@ function (bi::B200Integrator)(ss::Vector{State{Float64}}, tts::Vector{<:TransitO
         end
     end
     return out === nothing ? download!(p, ss, grad) : scatter!(ss, out, grad)
+end
+
+"""
+    chi2_fused(bi, ss, tts, t_obs, sigma; wrt_elements=false)
+
+The transit-timing run with the likelihood fused into the Jacobian kernel (nbg_transit_chi2_fused): returns `chi2[b]` and
+`grad[q,p,b]` = d chi2 / d q0 (or d / d elements when the states were built on the device; not reachable from a host-built State).
+`t_obs`, `sigma`: `ntt x n` (Julia `tt.tt'` order: slot k fastest within body i) shared by the batch.  No dtdq0 array exists anywhere.
+"""
+function chi2_fused(bi::B200Integrator, ss::Vector{State{Float64}}, tts::Vector{<:TransitTiming{Float64}}, t_obs::Matrix{Float64}, sigma::Matrix{Float64})
+    B, n = length(ss), ss[1].n
+    ntt, ti = tts[1].ntt, tts[1].ti
+    p = plan(n, B, bi.device)
+    upload(p, ss, true)
+    chi2 = zeros(Float64, B); g = zeros(Float64, 7, n, B); count = zeros(Int64, n, B)
+    chk(ccall((:nbg_transit_chi2_fused, LIB), Int32,
+              (Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
+              p, bi.h, bi.tmax, ti - 1, fill(Int32(ntt), n), t_obs, sigma, 0, 0, 1, chi2, g, count, C_NULL))
+    for (b, tt) in enumerate(tts); tt.count .= @view count[:, b]; end
+    download!(p, ss, true)
+    return chi2, g
 end
 
 # single-system forms: a batch of one

@@ -1,16 +1,21 @@
 // libnbgrad_b200.so — kernels and C ABI (include/nbgrad.h).  sm_100a only; no CPU fallback.
 //
-// Pipeline per chunk of S steps (all on the plan's stream):
-//   traj_kernel      one THREAD per system: x, v (Kahan), dq/dh; writes the per-step operator stream, detects
-//                    transits (detect_transits!, timing.jl:3-29) and queues them with a snapshot of the state
-//   transit_kernel   one THREAD per queued transit: findtransit! Newton iterations (timing.jl:31-73), Jacobian-free
-//                    because x, v, dqdt never read jac_step; then the one final step (timing.jl:75-80) whose operator
-//                    stream is written for the Jacobian kernel
-//   jac_kernel       one thread per COLUMN of jac_step, matrix resident in shared memory for the chunk: applies the
-//                    operator stream; at each queued transit saves the matrix, applies the transit step, emits
-//                    dtbvdq! (timing.jl:155-194), restores
-// Data layout in HBM: trajectory state and operator stream are SoA with the system index fastest (lanes = systems,
-// coalesced); jac_step/jac_error are [sys][row 6N][col 7N] (column threads coalesce).
+// Pipeline per chunk of S steps:
+//   traj_kernel       one THREAD per system: x, v (Kahan); detects transits (detect_transits!, timing.jl:3-29) and queues them with a
+//                     snapshot of the state; main-loop steps leave only the scalars of each Kepler solve (split path)
+//   pair_op_kernel    one thread per (system, step, pair section): compute_jacobian_gamma! -> Kepler operator records
+//   phi_dense_kernel  dense phisalpha operator of every step
+//   transit_kernel    one THREAD per queued transit: findtransit! Newton iterations (timing.jl:31-73), Jacobian-free because x, v,
+//                     dqdt never read jac_step; then the one final step (timing.jl:75-80) whose operator records are written
+//   jac_rx_kernel     one block per system, jac_step + jac_error in REGISTERS for the whole chunk (two lanes per column), operator
+//                     block of a step staged in shared memory; at each queued transit saves the matrix, applies the transit step,
+//                     emits dtbvdq! (timing.jl:155-194) or accumulates the fused chi^2 gradient, restores.  (N = 15, 16: jac_kernel,
+//                     matrix in shared memory.)
+// The host loop (run_steps) reads the number of queued transits back after the trajectory kernel of every chunk: a queue that is too
+// small is grown and the chunk re-run from a saved trajectory state (no transit is ever dropped), and the per-transit buffers are sized
+// from the actual count.  One-shot calls stream every chunk's transit rows to the caller's host arrays while the next chunk computes.
+// Data layout in HBM: trajectory state SoA with the system index fastest (lanes = systems); operator stream tiled by 32 systems;
+// jac_step/jac_error [sys][row 6N][col 7N].
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -20,9 +25,16 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include "../../include/nbgrad.h"
-#include "nbg_jacobian_mma.cuh"
+#include "nbg_jacobian_rx.cuh"
+#ifdef NBG_EXPERIMENTS
+#include "nbg_jacobian_mma.cuh"   // DMMA Jacobian kernel: measured 12-18 % slower, kept as evidence
+#endif
 #include "nbg_ics.cuh"
 
 using namespace nbg;
@@ -48,22 +60,31 @@ struct TrajArrays {
 };
 
 struct EventQueue {
-  int32_t* n;  // number queued this chunk (may exceed cap: overflow)
+  int32_t* n;  // number queued this chunk (may exceed cap: the host then grows the queue and re-runs the chunk)
   int32_t cap;
   int32_t *sys, *step, *body, *k;
   double *dt0, *t;   // initial guess / time of the prior state
   double* snap;      // [12N][cap]  x, v, xe, ve
-  double* hdr;       // [8][cap]    dx, dy, dvx, dvy, 1/gdot, 1/vsky, dvdt, dt0_final  (written by transit_kernel)
-  double* stream;    // [step_fields][cap] operator stream of the final step
+  double* hdr;       // [HDR][cap]  dx, dy, dvx, dvy, 1/gdot, 1/vsky, dvdt, dt0_final, chi^2 weight, chi^2 term  (written by transit_kernel)
+  double* stream;    // [step_fields][nq] operator stream of the final step (sized from the actual count)
 };
+constexpr int HDR = 10;
 
 struct TransitOut {
-  double* tt;      // [sys][RT][C]
-  double* dtdq0;   // [sys][RT][M][C]
+  double* tt;      // dense: [sys][RT][C]; event rows: [slot][C]; null = not wanted
+  double* dtdq0;   // dense: [sys][RT][M][C]; event rows: [slot][M][C]; null = not wanted (fused chi^2)
   const int32_t* ntt_body;  // device [N]
   const int32_t* off;       // device [N]
   int32_t RT, C;            // C = 1 (TransitTiming) or 3 (TransitParameters)
+  int32_t ev_rows;          // 1: the output row of a transit is its queue slot (per-chunk compact buffers, scattered by the host)
+  // fused transit-time likelihood (nbg_transit_chi2_fused): observations and per-system accumulators; null = off
+  const double* tobs; const double* sigma; int32_t per_system;
+  double* chi2;    // [sys]
+  double* gq;      // [sys][M]
 };
+__device__ __forceinline__ size_t out_rec(const TransitOut& O, long sys, int body, int k, int slot) {
+  return O.ev_rows ? (size_t)slot : (size_t)sys * O.RT + O.off[body] + k;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Launch bounds: the light (split-path) instantiation is capped at 128 registers so that 4 blocks fit an SM: a thread owns
@@ -121,8 +142,7 @@ __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel
                   Q.snap[(size_t)(9 * n + q) * Q.cap + slot] = b.ve[q];
                 }
               } else {
-                slot = -1;
-                st |= NBG_ST_EVENT_OVERFLOW;
+                slot = -1;   // the host sees *Q.n > cap, grows the queue and re-runs the chunk (run_steps)
               }
             } else {
               st |= NBG_ST_NTT_OVERFLOW;
@@ -228,9 +248,24 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   const double dx = b.x[3 * j] - b.x[3 * ti], dy = b.x[3 * j + 1] - b.x[3 * ti + 1];
   const double dvx = b.v[3 * j] - b.v[3 * ti], dvy = b.v[3 * j + 1] - b.v[3 * ti + 1];
   const double vsky = sqrt(dvx * dvx + dvy * dvy), bsky2 = dx * dx + dy * dy;
-  const size_t rec = (size_t)sys * O.RT + O.off[j] + Q.k[e];
-  O.tt[rec * O.C] = Q.t[e] + dt0;
-  if (O.C == 3) { O.tt[rec * 3 + 1] = vsky; O.tt[rec * 3 + 2] = bsky2; }
+  const size_t rec = out_rec(O, sys, j, Q.k[e], e);
+  const double ttv = Q.t[e] + dt0;
+  if (O.tt) {
+    O.tt[rec * O.C] = ttv;
+    if (O.C == 3) { O.tt[rec * 3 + 1] = vsky; O.tt[rec * 3 + 2] = bsky2; }
+  }
+  // fused likelihood: residual of this transit against its observation slot; masked slots (sigma <= 0, non-finite t_obs) weigh nothing
+  double chiw = 0.0, chit = 0.0;
+  if (O.chi2) {
+    const size_t ob = (O.per_system ? (size_t)sys * O.RT : 0) + O.off[j] + Q.k[e];
+    const double sg = O.sigma[ob], to = O.tobs[ob];
+    if (sg > 0.0 && isfinite(to)) {
+      const double r = (ttv - to) / sg;
+      chit = r * r;
+      chiw = 2.0 * r / sg;
+    }
+    if (!GRAD) atomicAdd(&O.chi2[sys], chit);   // no Jacobian kernel follows: sum here
+  }
   if (GRAD) {
     const double gd = gdot(b, dq, ti, j);
     const double dvdt = (dvx * (dq[6 * j + 3] - dq[6 * ti + 3]) + dvy * (dq[6 * j + 4] - dq[6 * ti + 4])) / vsky;
@@ -238,6 +273,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
     const size_t cap = Q.cap;
     H[0 * cap + e] = dx; H[1 * cap + e] = dy; H[2 * cap + e] = dvx; H[3 * cap + e] = dvy;
     H[4 * cap + e] = 1.0 / gd; H[5 * cap + e] = 1.0 / vsky; H[6 * cap + e] = dvdt; H[7 * cap + e] = dt0;
+    H[8 * cap + e] = chiw; H[9 * cap + e] = chit;
   }
   if (st) atomicOr(&T.status[sys], st);
   atomicAdd(&counters[1], (unsigned long long)iter);
@@ -265,6 +301,7 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   for (size_t q = tid; q < jsz; q += nthr) { S.Jv[q] = Jv_g[sys * jsz + q]; S.Je[q] = Je_g[sys * jsz + q]; }
   __syncthreads();
   const size_t sf = step_fields(n);
+  double gacc = 0.0, cacc = 0.0;   // fused chi^2: gradient entry of column c / the system's chi^2 terms (thread 0), this chunk
   for (int s = 0; s < nsteps; ++s) {
     Src src{stream + tile_offset(sf, ld / TILE, (size_t)s, (size_t)sys), TILE, (size_t)(sys % TILE)};
     jac_apply_step(S, src, n, M, c, 0.5 * h, tid, nthr);
@@ -287,8 +324,10 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
           const double jx0 = S.Jv[(6 * j) * M + c] - S.Jv[(6 * ti) * M + c], jx1 = S.Jv[(6 * j + 1) * M + c] - S.Jv[(6 * ti + 1) * M + c];
           const double jv0 = S.Jv[(6 * j + 3) * M + c] - S.Jv[(6 * ti + 3) * M + c], jv1 = S.Jv[(6 * j + 4) * M + c] - S.Jv[(6 * ti + 4) * M + c];
           const double dtdq = -(jx0 * dvx + jx1 * dvy + jv0 * dx + jv1 * dy) * gdinv;
-          const size_t rec = (size_t)sys * O.RT + O.off[j] + Q.k[slot];
-          if (O.C == 1) {
+          const size_t rec = out_rec(O, sys, j, Q.k[slot], slot);
+          if (O.gq) { gacc = fma(Q.hdr[8 * cap + slot], dtdq, gacc); if (c == 0) cacc += Q.hdr[9 * cap + slot]; }
+          if (!O.dtdq0) {
+          } else if (O.C == 1) {
             O.dtdq0[rec * M + c] = dtdq;
           } else {
             const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
@@ -305,6 +344,10 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   }
   __syncthreads();
   for (size_t q = tid; q < jsz; q += nthr) { Jv_g[sys * jsz + q] = S.Jv[q]; Je_g[sys * jsz + q] = S.Je[q]; }
+  if (O.gq && evlist) {
+    if (c < M) O.gq[(size_t)sys * M + c] += gacc;
+    if (c == 0) O.chi2[sys] += cacc;
+  }
 }
 
 // Register-resident Jacobian kernel (N <= NBG_RX_MAX_BODIES = 12): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
@@ -357,6 +400,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
   int32_t slot = -1;
   uint32_t pend = 0;  // bodies with a queued transit at the end of step s (read at the start of the step, used at its end)
   bool in_event = false;
+  double gacc = 0.0, cacc = 0.0;  // fused chi^2 accumulators of this chunk (column c of the gradient; thread 0: the chi^2 terms)
   while (true) {
     double* const cur = (s & 1) ? buf1 : buf0;
     double h2;
@@ -402,8 +446,13 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
       const double mine = (half == 0) ? (d0 * dvx + d1 * dvy) : (d0 * dx + d1 * dy);
       const double other = shx(mine);
       const double dtdq = -(mine + other) * gdinv;  // meaningful in the x half
-      const size_t rec = (size_t)sys * O.RT + O.off[ev_i] + Q.k[slot];
-      if (O.C == 1) {
+      const size_t rec = out_rec(O, sys, ev_i, Q.k[slot], slot);
+      if (O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
+        gacc = fma(Q.hdr[8 * cap + slot], dtdq, gacc);
+        if (tid == 0) cacc += Q.hdr[9 * cap + slot];
+      }
+      if (!O.dtdq0) {
+      } else if (O.C == 1) {
         if (valid && half == 0) O.dtdq0[rec * M + c] = dtdq;
       } else {
         const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
@@ -439,8 +488,13 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
         Je_g[q] = S.je[b][k];
       }
   }
+  if (O.gq && evlist && live) {
+    if (valid && half == 0) O.gq[(size_t)sys * M + c] += gacc;
+    if (tid == 0) O.chi2[sys] += cacc;
+  }
 }
 
+#ifdef NBG_EXPERIMENTS
 // DMMA Jacobian kernel (nbg_jacobian_mma.cuh): one block per system, mma_warps(N) warps, two 8-column tiles per warp; the same
 // work-item loop, operator staging and transit handling as jac_rx_kernel.  No fast-kick pairs (those run jac_rx_kernel<KICK>).
 template <int N, int MB, int TPW>
@@ -509,7 +563,7 @@ __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
       // dtbvdq! (timing.jl:155-194): lane t = 0 holds rows x0, v0 and lane t = 1 rows x1, v1 of occultor ev_i minus transited body ti
       const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
       const double gdinv = Q.hdr[4 * cap + slot];
-      const size_t rec = (size_t)sys * O.RT + O.off[ev_i] + Q.k[slot];
+      const size_t rec = out_rec(O, sys, ev_i, Q.k[slot], slot);
 #pragma unroll
       for (int T = 0; T < TPW; ++T) {
         double jx = 0.0, jw = 0.0;
@@ -581,6 +635,7 @@ int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, double* J
   jac_mma_kernel<N, MB, TPW><<<(unsigned)(nsys - sys0), mma_warps(N, TPW) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, nsys, sys0);
   return 0;
 }
+#endif  // NBG_EXPERIMENTS
 
 // Split path, second stage: the Kepler operator records of the main steps.  One thread per (system, step, pair section);
 // the 32 lanes of a warp are the systems of one tile, so the section index (hence drift_first) is uniform in a warp and
@@ -738,6 +793,24 @@ __global__ void dtdelements_kernel(const double* __restrict__ dtdq0, const doubl
   }
 }
 
+// The same product for the event rows of one chunk (one-shot calls stream their outputs chunk by chunk): out[e] = rows[e] . jac_init[sys_e].
+// One block per queued transit, thread = output column; ascending-row accumulation as in dtdelements_kernel.
+__global__ void dtde_rows_kernel(const double* __restrict__ rows, const double* __restrict__ jac_init, double* __restrict__ out,
+                                 const int32_t* __restrict__ qsys, int nq, int M, int C) {
+  extern __shared__ double rw[];  // this transit's dtdq0 row, M * C doubles
+  const int e = blockIdx.x;
+  if (e >= nq) return;
+  for (int q = threadIdx.x; q < M * C; q += blockDim.x) rw[q] = rows[(size_t)e * M * C + q];
+  __syncthreads();
+  const double* __restrict__ ji = jac_init + (size_t)qsys[e] * M * M;
+  for (int idx = threadIdx.x; idx < M * C; idx += blockDim.x) {
+    const int comp = idx % C, col = idx / C;
+    double acc = 0.0;
+    for (int row = 0; row < M; ++row) acc += rw[row * C + comp] * __ldg(ji + (size_t)col * M + row);
+    out[(size_t)e * M * C + idx] = acc;
+  }
+}
+
 // Fused transit-time likelihood: chi^2 = sum ((tt - t_obs) / sigma)^2 over the stored transits of one system and
 // its gradients with respect to the initial Cartesian coordinates (dtdq0) and to the orbital elements (dtdelements), reduced on
 // the device: 1 + 2M doubles per system leave the GPU instead of the full dtdq0 / dtdelements arrays.  One block per system, one
@@ -865,35 +938,62 @@ struct DevBuf {
     bytes = b;
     return 0;
   }
+  // per-chunk buffers sized from a measured count: grow with headroom so that a slowly rising count does not reallocate every chunk
+  int ensure_grow(size_t b) { return b <= bytes ? 0 : ensure(b + b / 4 + 4096); }
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
   template <class T> T* as() const { return (T*)p; }
+};
+struct PinBuf {  // pinned host memory
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t b) {
+    if (b <= bytes) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    b += b / 4 + 4096;
+    if (cudaHostAlloc(&p, b, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
+    bytes = b;
+    return 0;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
 };
 
 }  // namespace
 
 struct nbg_plan {
+  // multi-device plan (nbg_plan_create_multi): the parent only holds its children, one per device slice, and the first system of each
+  std::vector<nbg_plan*> kids;
+  std::vector<long> kid_lo;
   int n = 0, device = 0;
   long nsys = 0;
   size_t ld = 0;
   int64_t stream_budget = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;  // uploads that overlap the stepping (jac_init)
+  cudaStream_t copy_stream = nullptr;  // uploads that overlap the stepping (jac_init) and the per-chunk output copies
   cudaEvent_t copy_done = nullptr;
   cudaStream_t aux_stream = nullptr;   // operator kernels of the main steps, concurrent with the transit refinement
-  cudaEvent_t ev_traj = nullptr, ev_ops = nullptr, ev_ops2 = nullptr;
+  cudaEvent_t ev_traj = nullptr, ev_ops = nullptr, ev_ops2 = nullptr, ev_chunk = nullptr;
   cudaStream_t aux2_stream = nullptr;  // NBG_OVERLAP=2: the dense phisalpha operators on a third stream
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
+  DevBuf bbackup;  // trajectory state at the start of a chunk: a chunk whose transit queue overflowed is re-run from it
   DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
   DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters, belem;
+  DevBuf bevtt, bevd, beve;            // event-row outputs of one chunk (one-shot calls)
+  DevBuf bchi2, bgq, btobs, bsigma;    // fused likelihood
   DevBuf stage[8];  // staging for host<->device conversions
+  PinBuf hqn;       // queued-transit count of the chunk, read back after the trajectory kernel
+  PinBuf hstage[3]; // pinned staging of three chunks' transit rows in flight (copy / scatter / free)
+  cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> tev;  // timing events, created once and reused by every call (Timer)
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true, overlap3 = false;
   uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
   int phi_cached = 2;  // NBG_PHI_CACHED: 0 = phi_dense_kernel without the shared-memory cache of the per-pair tensors, 1 = T / gam cached, 2 = all pair fields
-  int jac_mma = 0;  // NBG_JAC_MMA: DMMA Jacobian kernel (nbg_jacobian_mma.cuh) for N = 8, measured 12-18 % slower than jac_rx_kernel; 1: two tiles per warp, 2: one
+  int jac_mma = 0;     // NBG_JAC_MMA (NBG_EXPERIMENTS builds only): DMMA Jacobian kernel for N = 8, measured 12-18 % slower than jac_rx_kernel
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
+  long queue_cap0 = 0; // NBG_QUEUE_CAP0: initial transit-queue capacity (tests force it tiny to exercise the re-run)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
   bool have_transit = false, have_dtde = false, transit_grad = false;
@@ -901,15 +1001,21 @@ struct nbg_plan {
   unsigned long long counters_host[8] = {0};
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long launches = 0;
-  // Host destinations of the transit outputs, known up front in the one-shot nbg_transit_timing call: the Jacobian kernel of the
-  // LAST chunk is launched in `slices` slices of the batch, and every finished slice (whose tt / dtdq0 rows are final) gets its
-  // dtdelements and its device-to-host copies on the copy stream while the next slice computes.
-  struct OutSink { double* tt = nullptr; double* dtdq0 = nullptr; double* dtde = nullptr; int slices = 0; bool want_dtde = false, delivered = false; };
-  OutSink sink;
-  int out_slices = 8;        // NBG_OUT_SLICES (<= 1: copy everything after the last kernel)
-  long out_slice_min = 4096; // NBG_OUT_SLICE_MIN: smallest batch that is sliced
-  std::vector<cudaEvent_t> ev_slice;   // one per slice, created on first use
-  bool trace = false;                  // NBG_TRACE=1: host wall-clock of the stages of the one-shot calls on stderr
+  long chunk_retries = 0;      // chunks re-run because the transit queue was too small
+  int64_t generation = 0;      // bumped whenever the resident state changes (callers that cache residency compare it)
+  // Output mode of the transit driver for the current call.
+  //  dense  : tt / dtdq0 / dtdelements as full device arrays [sys][RT]... (nbg_transit_timing_resident + nbg_transit_fetch)
+  //  rows   : per-chunk compact rows, one per queued transit, copied to pinned staging on the copy stream and scattered into the
+  //           caller's host arrays while the following chunks compute (nbg_transit_timing, host buffers known up front)
+  //  fused  : chi^2 and its gradient accumulated in the Jacobian kernel; no per-transit gradient rows exist anywhere
+  struct Sink { double* tt = nullptr; double* dtdq0 = nullptr; double* dtde = nullptr; bool want_dtde = false, active = false; };
+  Sink sink;
+  bool fused = false, fused_tt = false;
+  int fused_per_system = 0;
+  struct Job { int buf; int nq; };
+  std::deque<Job> jobs;        // chunks whose rows are in pinned staging, not yet scattered
+  long chunk_seq = 0;
+  bool trace = false;          // NBG_TRACE=1: host wall-clock of the stages of the one-shot calls on stderr
 };
 static double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -917,14 +1023,13 @@ namespace {
 
 int alloc_state(nbg_plan* p) {
   const size_t ld = p->ld, n = p->n;
-  const size_t M = 7 * n;
   int bad = 0;
   bad |= p->bx.ensure(3 * n * ld * 8); bad |= p->bv.ensure(3 * n * ld * 8); bad |= p->bxe.ensure(3 * n * ld * 8); bad |= p->bve.ensure(3 * n * ld * 8);
   bad |= p->bm.ensure(n * ld * 8); bad |= p->bdq.ensure(6 * n * ld * 8); bad |= p->bgs.ensure(n * ld * 8); bad |= p->bt.ensure(ld * 8);
   bad |= p->bterr.ensure(ld * 8); bad |= p->bcount.ensure(n * ld * 4); bad |= p->bstatus.ensure(ld * 4);
   bad |= p->bcounters.ensure(8 * 8); bad |= p->bntt.ensure(NBG_MAX_BODIES * 4); bad |= p->boff.ensure(NBG_MAX_BODIES * 4);
   bad |= p->qn.ensure(4);
-  (void)M;
+  bad |= p->hqn.ensure(64);
   if (bad) return -1;
   p->T = TrajArrays{p->bx.as<double>(), p->bv.as<double>(), p->bxe.as<double>(), p->bve.as<double>(), p->bm.as<double>(), p->bdq.as<double>(),
                     p->bgs.as<double>(), p->bt.as<double>(), p->bcount.as<int32_t>(), p->bstatus.as<uint32_t>(), ld};
@@ -937,37 +1042,41 @@ size_t jac_smem_bytes(int n, bool stage_phi) {
   return d * 8;
 }
 
-// a pair of timing events that is destroyed on every exit path
-struct EventPair {
-  cudaEvent_t a = nullptr, b = nullptr;
-  bool live = true;
-  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
-  ~EventPair() { if (live) { cudaEventDestroy(a); cudaEventDestroy(b); } }
-  EventPair(const EventPair&) = delete;
-  EventPair& operator=(const EventPair&) = delete;
-};
-
+// Per-kernel device times of one call: pairs of events from the plan's pool (created on first use, destroyed with the plan).
 struct Timer {
+  nbg_plan* p;
   cudaStream_t s;
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+  size_t first, used = 0;
+  std::vector<int> kinds;
   cudaStream_t cur = nullptr;
-  void begin(int kind, cudaStream_t on = nullptr) {
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    cur = on ? on : s;
-    cudaEventRecord(a, cur);
-    ev.push_back({kind, {a, b}});
-  }
-  void end() { cudaEventRecord(ev.back().second.second, cur); }
-  ~Timer() { for (auto& e : ev) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); } }
-  void collect(double* ms4) {
-    for (auto& e : ev) {
-      float t = 0;
-      cudaEventElapsedTime(&t, e.second.first, e.second.second);
-      ms4[e.first] += t;
-      cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+  explicit Timer(nbg_plan* plan) : p(plan), s(plan->stream), first(0) {}
+  cudaEvent_t ev(size_t k) {
+    while (p->tev.size() <= k) {
+      cudaEvent_t e = nullptr;
+      cudaEventCreate(&e);
+      p->tev.push_back(e);
     }
-    ev.clear();
+    return p->tev[k];
+  }
+  // the first pair brackets the whole call
+  void start() { cudaEventRecord(ev(0), s); used = 2; }
+  void stop() { cudaEventRecord(ev(1), s); }
+  void begin(int kind, cudaStream_t on = nullptr) {
+    cur = on ? on : s;
+    cudaEventRecord(ev(used), cur);
+    kinds.push_back(kind);
+    used += 2;
+  }
+  void end() { cudaEventRecord(ev(used - 1), cur); }
+  void collect(double* ms8) {
+    for (size_t q = 0; q < kinds.size(); ++q) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, ev(2 + 2 * q), ev(3 + 2 * q)) == cudaSuccess) ms8[kinds[q]] += t;
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ev(0), ev(1));
+    ms8[4] = tot;
+    cudaGetLastError();
   }
 };
 
@@ -978,16 +1087,49 @@ double check_step(double t0, double tmax) {  // Integrator.jl:249-259
   return -1 * sg(tmax);
 }
 
-// systems [lo, hi) are final (their Jacobian slice and their dtdelements ran on the main stream before ev_slice[k]): their rows of
-// tt / dtdq0 / dtdelements go to the host on the copy stream, concurrently with the next slice's kernels
-int deliver_slice(nbg_plan* p, int k, long lo, long hi) {
-  const size_t M = 7 * (size_t)p->n, C = p->C, RT = p->RT, cnt = (size_t)(hi - lo);
-  CK(cudaStreamWaitEvent(p->copy_stream, p->ev_slice[k], 0));
-  const size_t t0 = (size_t)lo * RT * C, q0 = t0 * M;
-  if (p->sink.tt) CK(cudaMemcpyAsync(p->sink.tt + t0, p->btt.as<double>() + t0, cnt * RT * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
-  if (p->sink.dtdq0) CK(cudaMemcpyAsync(p->sink.dtdq0 + q0, p->bdtdq0.as<double>() + q0, cnt * RT * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
-  if (p->sink.dtde && p->sink.want_dtde)
-    CK(cudaMemcpyAsync(p->sink.dtde + q0, p->bdtde.as<double>() + q0, cnt * RT * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+inline long round32(long v) { return (v + 31) / 32 * 32; }
+
+// ---- per-chunk output rows -> caller's arrays ----------------------------------------------------------------------------------
+// Staging layout of one chunk with nq queued transits (nqp = nq rounded up to 32):
+//   int32 sys[nqp], body[nqp], k[nqp] | double tt[nq][C] | dtdq0[nq][M][C] | dtdelements[nq][M][C]
+struct StageLayout {
+  size_t o_sys, o_body, o_k, o_tt, o_d, o_e, total;
+  StageLayout(long nq, size_t M, size_t C, bool grad, bool dtde) {
+    const size_t nqp = (size_t)round32(nq);
+    o_sys = 0; o_body = nqp * 4; o_k = 2 * nqp * 4;
+    o_tt = (3 * nqp * 4 + 7) / 8 * 8;
+    o_d = o_tt + (size_t)nq * C * 8;
+    o_e = o_d + (grad ? (size_t)nq * M * C * 8 : 0);
+    total = o_e + (dtde ? (size_t)nq * M * C * 8 : 0);
+  }
+};
+// the host half of the streaming: rows of a finished chunk into tt[sys][off[i]+k], dtdq0[sys][off[i]+k][...]
+int scatter_job(nbg_plan* p, const nbg_plan::Job& j) {
+  CK(cudaEventSynchronize(p->ev_copied[j.buf]));
+  const size_t M = 7 * (size_t)p->n, C = p->C, RT = p->RT, row = M * C;
+  const bool grad = p->sink.dtdq0 != nullptr, dtde = p->sink.want_dtde && p->sink.dtde != nullptr;
+  const StageLayout L(j.nq, M, C, p->transit_grad, p->sink.want_dtde);
+  const char* base = (const char*)p->hstage[j.buf].p;
+  const int32_t* sys = (const int32_t*)(base + L.o_sys);
+  const int32_t* body = (const int32_t*)(base + L.o_body);
+  const int32_t* k = (const int32_t*)(base + L.o_k);
+  const double* tt = (const double*)(base + L.o_tt);
+  const double* d = (const double*)(base + L.o_d);
+  const double* e = (const double*)(base + L.o_e);
+  for (long q = 0; q < j.nq; ++q) {
+    const size_t rec = (size_t)sys[q] * RT + p->off[body[q]] + k[q];
+    if (p->sink.tt) std::memcpy(p->sink.tt + rec * C, tt + (size_t)q * C, C * 8);
+    if (grad && p->transit_grad) std::memcpy(p->sink.dtdq0 + rec * row, d + (size_t)q * row, row * 8);
+    if (dtde) std::memcpy(p->sink.dtde + rec * row, e + (size_t)q * row, row * 8);
+  }
+  return 0;
+}
+// scatter finished chunks until at most `keep` remain in flight
+int drain_jobs(nbg_plan* p, size_t keep) {
+  while (p->jobs.size() > keep) {
+    if (int r = scatter_job(p, p->jobs.front())) return r;
+    p->jobs.pop_front();
+  }
   return 0;
 }
 
@@ -999,9 +1141,12 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   const int n = p->n;
   const long nsys = p->nsys;
   const size_t ld = p->ld;
+  const size_t M = 7 * (size_t)n, C = p->C;
   const bool kicks = p->kmask != 0u;
   const size_t sf = step_fields(n, kicks);
   const size_t jsz = (size_t)6 * n * 7 * n;
+  const bool rows = detect && p->sink.active;            // per-chunk event rows, streamed to the host
+  const bool fused = detect && grad && p->fused;        // chi^2 gradient accumulated in the Jacobian kernel
   // chunk length from the stream budget
   size_t per_step = sf * ld * 8;
   const size_t per_step_scal = p->split_traj ? (size_t)2 * npairs(n) * SCF * ld * 8 : 0;
@@ -1009,42 +1154,66 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   if (grad) {
     S = (long)std::max<int64_t>(1, std::min<int64_t>(p->stream_budget / (int64_t)(per_step + per_step_scal), 64));
     S = std::min(S, nsteps);
+    // equal chunks: 64 steps under a budget of 9 run as 8 x 8, not 7 x 9 + 1 (a one-step chunk pays a full Jacobian load/store)
+    const long nchunks = (nsteps + S - 1) / S;
+    S = (nsteps + nchunks - 1) / nchunks;
     if (p->bstream.ensure((size_t)S * per_step)) return fail(NBG_ERR_NOMEM, "operator stream allocation failed");
     if (per_step_scal && p->bscal.ensure((size_t)S * per_step_scal)) return fail(NBG_ERR_NOMEM, "scalar stream allocation failed");
   } else {
     S = std::min<long>(nsteps, 256);
   }
-  if (grad) {
-    // equal chunks: 64 steps under a budget of 9 run as 8 x 8, not 7 x 9 + 1 (a one-step chunk pays a full Jacobian load/store)
-    const long nchunks = (nsteps + S - 1) / S;
-    S = (nsteps + nchunks - 1) / nchunks;
-  }
   EventQueue Q{};
-  TransitOut O{};
   int32_t* evlist = nullptr;
   uint32_t* evmask = nullptr;
-  if (detect) {
-    double rate = std::min<double>(n - 1, rate_hint * 2.0 + 0.05);
-    long cap = (long)std::ceil((double)nsys * (double)S * rate) + 4096;
-    cap = std::min<long>(cap, (long)nsys * S * (n - 1));
-    cap = std::max<long>(cap, 32);
-    cap = (cap + 31) / 32 * 32;
+  // queue arrays that the trajectory kernel fills (sized by capacity); the per-transit operator stream and output rows are sized
+  // from the measured count after the trajectory kernel
+  auto alloc_queue = [&](long want) -> int {
+    long cap = std::min<long>(std::max<long>(want, 32), (long)nsys * S * (n - 1));
+    cap = round32(std::max<long>(cap, 32));
     int bad = 0;
     bad |= p->qsys.ensure(cap * 4); bad |= p->qstep.ensure(cap * 4); bad |= p->qbody.ensure(cap * 4); bad |= p->qk.ensure(cap * 4);
     bad |= p->qdt0.ensure(cap * 8); bad |= p->qt.ensure(cap * 8); bad |= p->qsnap.ensure((size_t)12 * n * cap * 8);
-    bad |= p->qhdr.ensure((size_t)8 * cap * 8);
-    if (grad) bad |= p->qstream.ensure(sf * (size_t)cap * 8);
-    bad |= p->bevlist.ensure((size_t)S * n * ld * 4);
-    bad |= p->bevmask.ensure((size_t)S * ld * 4);
-    if (bad) return fail(NBG_ERR_NOMEM, "event queue allocation failed");
+    bad |= p->qhdr.ensure((size_t)HDR * cap * 8);
+    if (bad) return fail(NBG_ERR_NOMEM, "transit queue allocation failed");
     Q = EventQueue{p->qn.as<int32_t>(), (int32_t)cap, p->qsys.as<int32_t>(), p->qstep.as<int32_t>(), p->qbody.as<int32_t>(), p->qk.as<int32_t>(),
                    p->qdt0.as<double>(), p->qt.as<double>(), p->qsnap.as<double>(), p->qhdr.as<double>(), p->qstream.as<double>()};
-    O = TransitOut{p->btt.as<double>(), p->bdtdq0.as<double>(), p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->RT, p->C};
+    return 0;
+  };
+  // trajectory state saved at the start of every chunk with detection: x, v, xe, ve, gsave, t, terr, count
+  const size_t bk_d = (size_t)(12 * n + n + 2) * ld;  // doubles
+  struct Seg { DevBuf* b; size_t bytes; };
+  const Seg segs[8] = {{&p->bx, 3 * (size_t)n * ld * 8}, {&p->bv, 3 * (size_t)n * ld * 8}, {&p->bxe, 3 * (size_t)n * ld * 8}, {&p->bve, 3 * (size_t)n * ld * 8},
+                       {&p->bgs, (size_t)n * ld * 8},    {&p->bt, ld * 8},                 {&p->bterr, ld * 8},               {&p->bcount, (size_t)n * ld * 4}};
+  auto backup = [&](bool restore) -> int {
+    char* bk = p->bbackup.as<char>();
+    size_t o = 0;
+    for (const Seg& sg : segs) {
+      if (restore) CK(cudaMemcpyAsync(sg.b->p, bk + o, sg.bytes, cudaMemcpyDeviceToDevice, p->stream));
+      else CK(cudaMemcpyAsync(bk + o, sg.b->p, sg.bytes, cudaMemcpyDeviceToDevice, p->stream));
+      o += sg.bytes;
+    }
+    return 0;
+  };
+  if (detect) {
+    long cap0 = p->queue_cap0;
+    if (cap0 <= 0) {  // heuristic from the caller's slot counts: twice the mean transit rate; wrong guesses only cost a re-run of the chunk
+      const double rate = std::min<double>(n - 1, rate_hint * 2.0 + 0.05);
+      cap0 = (long)std::ceil((double)nsys * (double)S * rate) + 4096;
+    }
+    if (int r = alloc_queue(cap0)) return r;
+    int bad = 0;
+    bad |= p->bevlist.ensure((size_t)S * n * ld * 4);
+    bad |= p->bevmask.ensure((size_t)S * ld * 4);
+    bad |= p->bbackup.ensure(bk_d * 8 + (size_t)n * ld * 4);
+    if (bad) return fail(NBG_ERR_NOMEM, "event list allocation failed");
     evlist = p->bevlist.as<int32_t>();
     evmask = p->bevmask.as<uint32_t>();
   }
   if (grad && detect) {
-    const size_t per_sys = std::max<size_t>(std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32), (size_t)8 * n * std::max(mma_warps(n, 2) * 2, mma_warps(n, 1)) * 16);
+    size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
+#ifdef NBG_EXPERIMENTS
+    per_sys = std::max<size_t>(per_sys, (size_t)8 * n * std::max(mma_warps(n, 2) * 2, mma_warps(n, 1)) * 16);
+#endif
     if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
   const bool use_rx = n <= NBG_RX_MAX_BODIES && (!p->force_generic_jac || kicks);
@@ -1060,46 +1229,68 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     CK(cudaFuncSetAttribute(jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   unsigned long long* dcount = p->bcounters.as<unsigned long long>();
+  bool waited_jinit = false;
+  int prev_buf = -1;  // staging buffer whose device-to-host copy may still read the event-row buffers
   long done = 0;
   while (done < nsteps) {
     const int s = (int)std::min<long>(S, nsteps - done);
-    if (detect) CK(cudaMemsetAsync(p->qn.p, 0, 4, p->stream));
-    tm.begin(0);
     double* tkerr = kahan_time ? p->bterr.as<double>() : nullptr;
     int s_split = 0;  // steps of this chunk whose Kepler records come from pair_op_kernel (split path)
-    if (grad && p->split_traj && !kicks) {
-      // dq/dh restarts from zero every step (ahl21.jl:9), so only the last step of the integration needs it: that step
-      // also evaluates the pair Jacobians in the trajectory thread (GRAD = true).  Every step's operator records come from
-      // pair_op_kernel, so jac_step does not depend on how the integration is cut into chunks or calls.
-      const bool last_chunk = done + s == nsteps;
-      const int s_light = last_chunk ? s - 1 : s;
-      s_split = s;
-      if (s_light > 0)
-        traj_kernel<false, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s_light, p->bstream.as<double>(), p->bscal.as<double>(), detect, ti, t0,
-                                                          done, h_intr, p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
-      if (s_light < s) {
-        const size_t o = (size_t)s_light;
-        traj_kernel<true, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s - s_light, p->bstream.as<double>() + o * sf * ld,
-                                                         p->bscal.as<double>() + o * 2 * npairs(n) * SCF * ld, detect, ti, t0, done + s_light, h_intr,
-                                                         p->bntt.as<int32_t>(), Q, evlist ? evlist + o * n * ld : nullptr,
-                                                         evmask ? evmask + o * ld : nullptr, kahan_time, tkerr, p->kmask);
-        if (s_light > 0) p->launches++;
+    long nq = 0;
+    for (int attempt = 0;; ++attempt) {
+      if (detect) {
+        if (int r = backup(attempt > 0)) return r;
+        CK(cudaMemsetAsync(p->qn.p, 0, 4, p->stream));
       }
-    } else if (grad && kicks) {
-      traj_kernel<true, 1, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
-                                                             p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
-    } else if (grad) {
-      traj_kernel<true, 1><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
-                                                       p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
-    } else if (kicks) {
-      traj_kernel<false, 0, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr,
-                                                              p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
-    } else {
-      traj_kernel<false, 0><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
-                                                         Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+      tm.begin(0);
+      if (grad && p->split_traj && !kicks) {
+        // dq/dh restarts from zero every step (ahl21.jl:9), so only the last step of the integration needs it: that step
+        // also evaluates the pair Jacobians in the trajectory thread (GRAD = true).  Every step's operator records come from
+        // pair_op_kernel, so jac_step does not depend on how the integration is cut into chunks or calls.
+        const bool last_chunk = done + s == nsteps;
+        const int s_light = last_chunk ? s - 1 : s;
+        s_split = s;
+        if (s_light > 0)
+          traj_kernel<false, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s_light, p->bstream.as<double>(), p->bscal.as<double>(), detect, ti, t0,
+                                                            done, h_intr, p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+        if (s_light < s) {
+          const size_t o = (size_t)s_light;
+          traj_kernel<true, 2><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s - s_light, p->bstream.as<double>() + o * sf * ld,
+                                                           p->bscal.as<double>() + o * 2 * npairs(n) * SCF * ld, detect, ti, t0, done + s_light, h_intr,
+                                                           p->bntt.as<int32_t>(), Q, evlist ? evlist + o * n * ld : nullptr,
+                                                           evmask ? evmask + o * ld : nullptr, kahan_time, tkerr, p->kmask);
+          if (s_light > 0) p->launches++;
+        }
+      } else if (grad && kicks) {
+        traj_kernel<true, 1, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
+                                                               p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+      } else if (grad) {
+        traj_kernel<true, 1><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, p->bstream.as<double>(), nullptr, detect, ti, t0, done, h_intr,
+                                                         p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+      } else if (kicks) {
+        traj_kernel<false, 0, true><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr,
+                                                                p->bntt.as<int32_t>(), Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+      } else {
+        traj_kernel<false, 0><<<gridA, tpb, 0, p->stream>>>(p->T, n, nsys, h, s, nullptr, nullptr, detect, ti, t0, done, h_intr, p->bntt.as<int32_t>(),
+                                                           Q, evlist, evmask, kahan_time, tkerr, p->kmask);
+      }
+      tm.end();
+      p->launches++;
+      if (!detect) break;
+      // While the GPU finishes the previous chunk and runs this trajectory kernel, the host scatters the rows of the chunk before
+      // the previous one (its copy finished long ago) into the caller's arrays.
+      if (attempt == 0 && rows) if (int r = drain_jobs(p, 1)) return r;
+      int32_t* hq = (int32_t*)p->hqn.p;
+      CK(cudaMemcpyAsync(hq, Q.n, 4, cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaStreamSynchronize(p->stream));
+      nq = *hq;
+      if (nq <= Q.cap) break;
+      // more transits than the queue holds: nothing of this chunk has been consumed yet, so grow the queue to the measured count
+      // and run the trajectory kernel again from the saved state (deterministic: the same nq transits are found)
+      if (attempt >= 2) return fail(NBG_ERR_CUDA, "transit queue overflow persists after the re-run");
+      p->chunk_retries++;
+      if (int r = alloc_queue(nq + 32)) return r;
     }
-    tm.end();
-    p->launches++;
     // The operator kernels of the main steps (pair_op, phi_dense) depend only on the trajectory kernel; they run on the aux
     // stream next to the transit refinement (latency-bound, few threads) and join before the Jacobian kernel.
     const bool fork = grad && (s_split > 0 || use_rx) && p->overlap;
@@ -1127,20 +1318,59 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       if (fork3) CK(cudaEventRecord(p->ev_ops2, aux2));
     }
     if (fork) CK(cudaEventRecord(p->ev_ops, aux));
+    TransitOut O{};
+    int buf = -1;
     if (detect) {
-      tm.begin(1);
-      const unsigned gridT = (unsigned)((Q.cap + tpb - 1) / tpb);
-      if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
-      else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
-      else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
-      else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
-      tm.end();
-      p->launches++;
-      if (grad && use_rx) {
-        tm.begin(5);
-        if (launch_phi_dense(p->stream, n, Q.stream, 0, Q.cap, Q.n, 1, kicks, p->phi_cached)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+      // per-transit buffers from the measured count
+      const size_t nqp = (size_t)round32(std::max<long>(nq, 1));
+      if (grad && p->qstream.ensure_grow(sf * nqp * 8)) return fail(NBG_ERR_NOMEM, "transit operator stream allocation failed");
+      Q.stream = p->qstream.as<double>();
+      O = TransitOut{p->btt.as<double>(), grad ? p->bdtdq0.as<double>() : nullptr, p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->RT, p->C, 0,
+                     nullptr, nullptr, 0, nullptr, nullptr};
+      if (rows) {
+        int bad = p->bevtt.ensure_grow(nqp * C * 8);
+        if (grad) bad |= p->bevd.ensure_grow(nqp * M * C * 8);
+        if (grad && p->sink.want_dtde) bad |= p->beve.ensure_grow(nqp * M * C * 8);
+        buf = (int)(p->chunk_seq % 3);
+        const StageLayout L(nq, M, C, grad, grad && p->sink.want_dtde);
+        bad |= p->hstage[buf].ensure(L.total + 64);
+        if (bad) return fail(NBG_ERR_NOMEM, "transit row buffers allocation failed");
+        O.tt = p->bevtt.as<double>();
+        O.dtdq0 = grad ? p->bevd.as<double>() : nullptr;
+        O.ev_rows = 1;
+        // the previous chunk's rows may still be on their way to the host
+        if (prev_buf >= 0) CK(cudaStreamWaitEvent(p->stream, p->ev_copied[prev_buf], 0));
+        if (nq > 0) {  // who the rows belong to: copied now, before the next trajectory kernel reuses the queue
+          char* hb = (char*)p->hstage[buf].p;
+          CK(cudaMemcpyAsync(hb + L.o_sys, Q.sys, (size_t)nq * 4, cudaMemcpyDeviceToHost, p->stream));
+          CK(cudaMemcpyAsync(hb + L.o_body, Q.body, (size_t)nq * 4, cudaMemcpyDeviceToHost, p->stream));
+          CK(cudaMemcpyAsync(hb + L.o_k, Q.k, (size_t)nq * 4, cudaMemcpyDeviceToHost, p->stream));
+        }
+      } else if (fused) {
+        O.tt = p->fused_tt ? p->btt.as<double>() : nullptr;
+        O.dtdq0 = nullptr;
+        O.tobs = p->btobs.as<double>(); O.sigma = p->bsigma.as<double>(); O.per_system = p->fused_per_system;
+        O.chi2 = p->bchi2.as<double>(); O.gq = p->bgq.as<double>();
+      } else if (p->fused) {  // chi^2 only (grad = 0): summed by the transit kernel
+        O.tt = p->fused_tt ? p->btt.as<double>() : nullptr;
+        O.tobs = p->btobs.as<double>(); O.sigma = p->bsigma.as<double>(); O.per_system = p->fused_per_system;
+        O.chi2 = p->bchi2.as<double>();
+      }
+      if (nq > 0) {
+        tm.begin(1);
+        const unsigned gridT = (unsigned)((nq + tpb - 1) / tpb);
+        if (grad && kicks) transit_kernel<true, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+        else if (grad) transit_kernel<true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+        else if (kicks) transit_kernel<false, true><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
+        else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
         tm.end();
         p->launches++;
+        if (grad && use_rx) {
+          tm.begin(5);
+          if (launch_phi_dense(p->stream, n, Q.stream, 0, nq, nullptr, 1, kicks, p->phi_cached)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
+          tm.end();
+          p->launches++;
+        }
       }
     }
     if (fork) CK(cudaStreamWaitEvent(p->stream, p->ev_ops, 0));
@@ -1155,69 +1385,36 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>(), *Jb = p->bJbak.as<double>();
         const double* strm = p->bstream.as<double>();
         int rc = 0;
-        // last chunk of a call whose host outputs are known (p->sink): slices of the batch, each followed by its output copies
-        const int K = (p->sink.slices > 1 && detect && !kicks && done + s == nsteps) ? p->sink.slices : 1;
-        bool waited_jinit = false;
+        const long hi = nsys, lo = 0;
         if (kicks) rc = launch_jac_rx_kicked(n, p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, p->kmask);
-        else for (int k = 0; k < K && !rc; ++k) {
-          const long lo = (nsys / TILE) * k / K * TILE, hi = k + 1 == K ? nsys : (nsys / TILE) * (k + 1) / K * TILE;
-          if (hi <= lo) continue;
-          switch (n) {
-            case 2: rc = launch_jac_rx<2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 3: rc = launch_jac_rx<3, 3>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 4: rc = launch_jac_rx<4, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 5: rc = launch_jac_rx<5, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 6: rc = launch_jac_rx<6, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 7: rc = launch_jac_rx<7, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 9: rc = launch_jac_rx<9, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 10:  // two blocks of 5 warps per SM at 168 registers (spills ~45 doubles): measured 1.25x faster than one block at 255 (NBG_RX_UNROLL=21)
-              if (p->rx_unroll == 21) rc = launch_jac_rx<10, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else rc = launch_jac_rx<10, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              break;
-            case 11: rc = launch_jac_rx<11, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 12: rc = launch_jac_rx<12, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 13: rc = launch_jac_rx<13, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            case 14: rc = launch_jac_rx<14, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-            default:
-              if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
-              if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
-              // NBG_RX_UNROLL: 38 (default) = full unroll, no per-group barrier, 2 blocks/SM at 255 registers; 22 = pivot blocks of 2 with a barrier per
-              // group; 48 = two systems per block in lockstep; anything else = pivot blocks of 2 at 3 blocks/SM.  (The other combinations of
-              // pivots per block / barrier / blocks per SM were measured in r01c-r01h and removed: DESIGN.md 5, "measured and rejected".)
-              if (p->rx_unroll == 22) rc = launch_jac_rx<8, 2, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 48) rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else if (p->rx_unroll == 38) rc = launch_jac_rx<8, 8, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              else rc = launch_jac_rx<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
-              break;
-          }
-          if (!rc && K > 1) {
-            while ((int)p->ev_slice.size() <= k) {
-              cudaEvent_t e;
-              CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-              p->ev_slice.push_back(e);
-            }
-            if (p->sink.want_dtde) {  // dtdelements of the slice right behind its Jacobian kernel (jac_init: uploaded on the copy stream)
-              const size_t M = 7 * (size_t)n;
-              if (!waited_jinit) { CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0)); waited_jinit = true; }
-              CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * (M | 1) * 8)));
-              dtdelements_kernel<<<(unsigned)(hi - lo), 256, M * (M | 1) * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(),
-                                                                                        p->bdtde.as<double>(), p->bcount.as<int32_t>(),
-                                                                                        p->bntt.as<int32_t>(), p->boff.as<int32_t>(), n, ld, p->RT, p->C, lo);
-              p->launches++;
-            }
-            CK(cudaEventRecord(p->ev_slice[k], p->stream));
-          }
-        }
-        if (K > 1 && !rc) {
-          // every slice is in flight before the first copy is issued: a pageable destination makes cudaMemcpyAsync block the host,
-          // which must not delay the launches
-          tm.end();
-          for (int k = 0; k < K; ++k) {
-            const long lo = (nsys / TILE) * k / K * TILE, hi = k + 1 == K ? nsys : (nsys / TILE) * (k + 1) / K * TILE;
-            if (hi > lo) if (int r = deliver_slice(p, k, lo, hi)) return r;
-          }
-          tm.begin(2);
-          p->sink.delivered = true;
+        else switch (n) {
+          case 2: rc = launch_jac_rx<2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 3: rc = launch_jac_rx<3, 3>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 4: rc = launch_jac_rx<4, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 5: rc = launch_jac_rx<5, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 6: rc = launch_jac_rx<6, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 7: rc = launch_jac_rx<7, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 9: rc = launch_jac_rx<9, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 10:  // two blocks of 5 warps per SM at 168 registers (spills ~45 doubles): measured 1.25x faster than one block at 255
+            rc = launch_jac_rx<10, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+            break;
+          case 11: rc = launch_jac_rx<11, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 12: rc = launch_jac_rx<12, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 13: rc = launch_jac_rx<13, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 14: rc = launch_jac_rx<14, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          default:
+#ifdef NBG_EXPERIMENTS
+            // measured and rejected: the DMMA kernel, pivot blocks of 2 with a barrier per group (22), two systems per block
+            // in lockstep (48), pivot blocks of 2 at 3 blocks/SM (other values)
+            if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
+            if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
+            if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break; }
+            if (p->rx_unroll == 48) { rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break; }
+            if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break; }
+#endif
+            // full unroll, no per-group barrier, 2 blocks/SM at 255 registers
+            rc = launch_jac_rx<8, 8, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+            break;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
       } else {
@@ -1227,11 +1424,34 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       tm.end();
       p->launches++;
     }
+    if (rows) {
+      // this chunk's rows: dtdelements of the rows, then everything to pinned staging on the copy stream while the next chunk computes
+      const StageLayout L(nq, M, C, grad, grad && p->sink.want_dtde);
+      if (nq > 0 && grad && p->sink.want_dtde) {
+        if (!waited_jinit) { CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0)); waited_jinit = true; }  // jac_init: uploaded / computed on the copy stream
+        dtde_rows_kernel<<<(unsigned)nq, 64, M * C * 8, p->stream>>>(p->bevd.as<double>(), p->bjinit.as<double>(), p->beve.as<double>(), Q.sys, (int)nq,
+                                                                      (int)M, (int)C);
+        p->launches++;
+      }
+      CK(cudaEventRecord(p->ev_chunk, p->stream));
+      CK(cudaStreamWaitEvent(p->copy_stream, p->ev_chunk, 0));
+      if (nq > 0) {
+        char* hb = (char*)p->hstage[buf].p;
+        CK(cudaMemcpyAsync(hb + L.o_tt, p->bevtt.p, (size_t)nq * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+        if (grad) CK(cudaMemcpyAsync(hb + L.o_d, p->bevd.p, (size_t)nq * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+        if (grad && p->sink.want_dtde) CK(cudaMemcpyAsync(hb + L.o_e, p->beve.p, (size_t)nq * M * C * 8, cudaMemcpyDeviceToHost, p->copy_stream));
+      }
+      CK(cudaEventRecord(p->ev_copied[buf], p->copy_stream));
+      p->jobs.push_back(nbg_plan::Job{buf, (int)nq});
+      prev_buf = buf;
+      p->chunk_seq++;
+    }
     CK(cudaGetLastError());
     done += s;
     p->counters_host[0] += (unsigned long long)nsys * s;
     if (grad) p->counters_host[5] += (unsigned long long)nsys * s;
   }
+  if (rows) if (int r = drain_jobs(p, 0)) return r;
   return 0;
 }
 
@@ -1256,12 +1476,39 @@ int pair_mask(const uint8_t* pair, int n, uint32_t* mask) {
   return 0;
 }
 
+// ---- multi-device plans -----------------------------------------------------------------------------------------------------------
+// f(kid, first system of its slice, systems in its slice) runs on one host thread per child plan (= per device slice); the first
+// failure (code and message) is reported to the caller's thread.
+template <class F> int for_kids(nbg_plan* p, F&& f) {
+  const size_t K = p->kids.size();
+  std::vector<int> rc(K, 0);
+  std::vector<std::string> err(K);
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < K; ++k)
+    th.emplace_back([&, k]() {
+      rc[k] = f(p->kids[k], p->kid_lo[k], p->kids[k]->nsys);
+      if (rc[k]) err[k] = g_err;
+    });
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < K; ++k)
+    if (rc[k]) return fail(rc[k], "device slice " + std::to_string(k) + ": " + err[k]);
+  return 0;
+}
+template <class T> T* at(T* base, size_t off) { return base ? base + off : nullptr; }
+
 }  // namespace
 
 extern "C" {
 
-int32_t nbg_version(void) { return 100; }
+int32_t nbg_version(void) { return 200; }
 const char* nbg_last_error(void) { return g_err.c_str(); }
+int32_t nbg_build_flags(void) {
+#ifdef NBG_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 int32_t nbg_device_count(void) {
   int c = 0;
   if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -1288,6 +1535,8 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   CK(cudaEventCreateWithFlags(&p->ev_traj, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&p->ev_ops, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&p->ev_ops2, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&p->ev_chunk, cudaEventDisableTiming));
+  for (auto& e : p->ev_copied) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&p->aux2_stream, cudaStreamNonBlocking));
   if (stream_budget_bytes <= 0) {
     size_t fr = 0, tot = 0;
@@ -1303,8 +1552,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_OVERLAP")) { p->overlap = (e[0] != '0'); p->overlap3 = (e[0] == '2'); }   // 0: operator kernels on the main stream (clean per-kernel times)
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
   if (const char* e = getenv("NBG_TRACE")) p->trace = (e[0] == '1');
-  if (const char* e = getenv("NBG_OUT_SLICES")) p->out_slices = std::max(1, std::min(64, atoi(e)));
-  if (const char* e = getenv("NBG_OUT_SLICE_MIN")) p->out_slice_min = std::max(1L, atol(e));
+  if (const char* e = getenv("NBG_QUEUE_CAP0")) p->queue_cap0 = std::max(0L, atol(e));
   if (alloc_state(p)) return fail(NBG_ERR_NOMEM, "state allocation failed");
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   guard.p = nullptr;
@@ -1312,18 +1560,62 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   return NBG_OK;
 }
 
+// One plan over several devices: contiguous slices of the batch, one child plan + one host thread per entry of
+// `devices`; every call on the parent runs on all slices concurrently and reads / writes the slices of the caller's arrays.  The
+// same device may be listed more than once (slices then share it).
+int32_t nbg_plan_create_multi(nbg_plan** out, int32_t nbody, int64_t nsys, const int32_t* devices, int32_t ndev, int64_t stream_budget_bytes) {
+  if (!out) return fail(NBG_ERR_ARG, "plan pointer is NULL");
+  *out = nullptr;
+  if (!devices || ndev < 1) return fail(NBG_ERR_ARG, "devices[ndev] is required");
+  if (nsys < ndev) return fail(NBG_ERR_ARG, "fewer systems than device slices");
+  if (ndev == 1) return nbg_plan_create(out, nbody, nsys, devices[0], stream_budget_bytes);
+  nbg_plan* p = new nbg_plan();
+  p->n = nbody; p->nsys = nsys; p->device = devices[0];
+  struct Guard { nbg_plan* p; ~Guard() { if (p) nbg_plan_destroy(p); } } guard{p};
+  for (int k = 0; k < ndev; ++k) {
+    const long lo = (long)(nsys * k / ndev), hi = (long)(nsys * (k + 1) / ndev);
+    int share = 0;
+    for (int q = 0; q < ndev; ++q) share += devices[q] == devices[k];
+    int64_t budget = stream_budget_bytes > 0 ? stream_budget_bytes / share : 0;
+    if (budget == 0 && share > 1) {  // the default (1/4 of the free memory) divided among the slices that share the device
+      int nd = nbg_device_count();
+      if (devices[k] < 0 || devices[k] >= nd) return fail(nd ? NBG_ERR_ARG : NBG_ERR_NO_DEVICE, nd ? "device index out of range" : "no CUDA device: libnbgrad_b200 has no CPU fallback");
+      CK(cudaSetDevice(devices[k]));
+      size_t fr = 0, tot = 0;
+      CK(cudaMemGetInfo(&fr, &tot));
+      budget = (int64_t)(tot / 4 / share);
+      budget = std::min<int64_t>(budget, (int64_t)(fr / 2));
+    }
+    nbg_plan* kid = nullptr;
+    if (int r = nbg_plan_create(&kid, nbody, hi - lo, devices[k], budget)) return r;
+    p->kids.push_back(kid);
+    p->kid_lo.push_back(lo);
+  }
+  guard.p = nullptr;
+  *out = p;
+  return NBG_OK;
+}
+
 int32_t nbg_plan_destroy(nbg_plan* p) {
   if (!p) return NBG_OK;
+  if (!p->kids.empty()) {
+    for (nbg_plan* k : p->kids) nbg_plan_destroy(k);
+    delete p;
+    return NBG_OK;
+  }
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   if (p->aux_stream) cudaStreamSynchronize(p->aux_stream);
   if (p->aux2_stream) cudaStreamSynchronize(p->aux2_stream);
-  DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bJv, &p->bJe, &p->bJbak,
-                   &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap, &p->qhdr, &p->qstream,
-                   &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters, &p->belem};
+  DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bbackup, &p->bJv, &p->bJe,
+                   &p->bJbak, &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap,
+                   &p->qhdr, &p->qstream, &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters, &p->belem, &p->bevtt, &p->bevd,
+                   &p->beve, &p->bchi2, &p->bgq, &p->btobs, &p->bsigma};
   for (auto* b : all) b->release();
   for (auto& b : p->stage) b.release();
+  for (auto& b : p->hstage) b.release();
+  p->hqn.release();
   if (p->stream) cudaStreamDestroy(p->stream);
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->copy_done) cudaEventDestroy(p->copy_done);
@@ -1332,8 +1624,10 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   if (p->ev_ops2) cudaEventDestroy(p->ev_ops2);
   if (p->ev_traj) cudaEventDestroy(p->ev_traj);
   if (p->ev_ops) cudaEventDestroy(p->ev_ops);
-  for (cudaEvent_t e : p->ev_slice) cudaEventDestroy(e);
-  p->ev_slice.clear();
+  if (p->ev_chunk) cudaEventDestroy(p->ev_chunk);
+  for (cudaEvent_t e : p->ev_copied) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->tev) cudaEventDestroy(e);
+  p->tev.clear();
   cudaGetLastError();
   delete p;
   return NBG_OK;
@@ -1341,6 +1635,10 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
 
 int32_t nbg_set_pair(nbg_plan* p, const uint8_t* pair) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) {
+    for (nbg_plan* k : p->kids) if (int r = nbg_set_pair(k, pair)) return r;
+    return NBG_OK;
+  }
   uint32_t mask = 0;
   if (int r = pair_mask(pair, p->n, &mask)) return r;
   p->kmask = mask;
@@ -1350,7 +1648,15 @@ int32_t nbg_set_pair(nbg_plan* p, const uint8_t* pair) {
 int32_t nbg_set_state(nbg_plan* p, const double* x, const double* v, const double* m, double t0, const double* xerror, const double* verror,
                       const double* jac_step, const double* jac_error, const double* dqdt) {
   if (!p || !x || !v || !m) return fail(NBG_ERR_ARG, "plan, x, v, m are required");
+  if (!p->kids.empty()) {
+    const size_t n = p->n, M = 7 * n;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_set_state(k, x + lo * 3 * n, v + lo * 3 * n, m + lo * n, t0, at(xerror, lo * 3 * n), at(verror, lo * 3 * n), at(jac_step, lo * M * M),
+                           at(jac_error, lo * M * M), at(dqdt, lo * M));
+    });
+  }
   CK(cudaSetDevice(p->device));
+  p->generation++;
   const size_t n = p->n, nsys = p->nsys, M = 7 * n;
   const double* src[6] = {x, v, m, xerror, verror, dqdt};
   const size_t cnt[6] = {3 * n, 3 * n, n, 3 * n, 3 * n, M};
@@ -1394,7 +1700,10 @@ int32_t nbg_set_state(nbg_plan* p, const double* x, const double* v, const doubl
 // State(ic::ElementsIC) on the device: init_nbody (src/ics/init_nbody.jl:13-27) for every system of the batch.
 int32_t nbg_set_state_elements(nbg_plan* p, const double* elements, const double* eps, double t0, int32_t want_jac_init) {
   if (!p || !elements) return fail(NBG_ERR_ARG, "plan and elements are required");
+  if (!p->kids.empty())
+    return for_kids(p, [&](nbg_plan* k, long lo, long) { return nbg_set_state_elements(k, elements + (size_t)lo * 7 * p->n, eps, t0, want_jac_init); });
   CK(cudaSetDevice(p->device));
+  p->generation++;
   const size_t n = p->n, nsys = p->nsys, M = 7 * n;
   IcsHierarchy H;
   std::memset(&H, 0, sizeof(H));
@@ -1453,6 +1762,10 @@ int32_t nbg_set_state_elements(nbg_plan* p, const double* elements, const double
 
 int32_t nbg_get_jac_init(nbg_plan* p, double* jac_init) {
   if (!p || !jac_init) return fail(NBG_ERR_ARG, "NULL argument");
+  if (!p->kids.empty()) {
+    const size_t M = 7 * (size_t)p->n;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) { return nbg_get_jac_init(k, jac_init + (size_t)lo * M * M); });
+  }
   if (!p->jinit_resident) return fail(NBG_ERR_ARG, "no device-computed jac_init (call nbg_set_state_elements with want_jac_init)");
   CK(cudaSetDevice(p->device));
   const size_t M = 7 * (size_t)p->n;
@@ -1474,7 +1787,15 @@ static int make_jac_identity(nbg_plan* p) {
 
 int32_t nbg_get_state(nbg_plan* p, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error, double* dqdt, double* t,
                       uint32_t* status) {
-  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) {
+    const size_t n = p->n, M = 7 * n;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_get_state(k, at(x, lo * 3 * n), at(v, lo * 3 * n), at(xerror, lo * 3 * n), at(verror, lo * 3 * n), at(jac_step, lo * M * M),
+                           at(jac_error, lo * M * M), at(dqdt, lo * M), at(t, lo), at(status, lo));
+    });
+  }
+  if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
   CK(cudaSetDevice(p->device));
   const size_t n = p->n, nsys = p->nsys, M = 7 * n;
   double* outs[5] = {x, v, xerror, verror, dqdt};
@@ -1509,32 +1830,29 @@ int32_t nbg_get_state(nbg_plan* p, double* x, double* v, double* xerror, double*
   return NBG_OK;
 }
 
-static void finish_timings(nbg_plan* p, Timer& tm, EventPair& ev) {
-  cudaEvent_t e0 = ev.a, e1 = ev.b;
+static void finish_timings(nbg_plan* p, Timer& tm) {
   for (double& q : p->timings) q = 0;
   tm.collect(p->timings);
-  float tot = 0;
-  cudaEventElapsedTime(&tot, e0, e1);
-  p->timings[4] = tot;
+  const double tot = p->timings[4];
   // pair_op / phi_dense run on the aux stream concurrently with the transit kernel, so the per-kernel times can add up to more
   // than the total; "other" is what is left of the total, never negative
   p->timings[3] = std::max(0.0, tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6]);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);
   for (int q = 1; q <= 4; ++q) p->counters_host[q] = dc[q];
-  p->counters_host[5] = p->counters_host[5];
 }
 
 int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_last, int32_t grad, int32_t time_mode, double t_final) {
-  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) return for_kids(p, [&](nbg_plan* k, long, long) { return nbg_integrate_resident(k, h, nsteps, h_last, grad, time_mode, t_final); });
+  if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
   if (nsteps < 0) return fail(NBG_ERR_ARG, "nsteps must be >= 0");
   CK(cudaSetDevice(p->device));
+  p->generation++;
   if (grad) if (int r = make_jac_identity(p)) return r;
   if (time_mode == 0) CK(cudaMemsetAsync(p->bterr.p, 0, p->ld * 8, p->stream));  // s2 = zero(T): Integrator.jl:212
-  Timer tm{p->stream};
-  EventPair ev;
-  cudaEvent_t e0 = ev.a, e1 = ev.b;
-  cudaEventRecord(e0, p->stream);
+  Timer tm(p);
+  tm.start();
   if (int r = run_steps(p, h, (long)nsteps, grad != 0, false, 0, 0.0, h, time_mode == 0, tm, 0.0)) return r;
   if (h_last != 0.0)
     if (int r = run_steps(p, h_last, 1, grad != 0, false, 0, 0.0, h_last, time_mode == 0, tm, 0.0)) return r;
@@ -1543,9 +1861,9 @@ int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_l
     CK(cudaMemcpyAsync(p->bt.p, tv.data(), p->nsys * 8, cudaMemcpyHostToDevice, p->stream));
     CK(cudaStreamSynchronize(p->stream));
   }
-  cudaEventRecord(e1, p->stream);
+  tm.stop();
   CK(cudaStreamSynchronize(p->stream));
-  finish_timings(p, tm, ev);
+  finish_timings(p, tm);
   CK(cudaGetLastError());
   return NBG_OK;
 }
@@ -1553,9 +1871,23 @@ int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_l
 // (intr)(s, o::CartesianOutput) (Outputs.jl:26-49) without the per-step host round trip: positions and velocities before every
 // `stride`-th step are collected on the device and copied out once.
 int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples) {
-  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
   if (nsteps < 1 || stride < 1 || !x_samples || !v_samples) return fail(NBG_ERR_ARG, "nsteps >= 1, stride >= 1 and both sample buffers are required");
+  if (!p->kids.empty()) {  // a slice's samples are [k][its systems]: collected per slice, then interleaved into [k][all systems]
+    const size_t n3 = 3 * (size_t)p->n, nsamp = (size_t)((nsteps + stride - 1) / stride), B = (size_t)p->nsys;
+    return for_kids(p, [&](nbg_plan* k, long lo, long cnt) {
+      std::vector<double> xs(nsamp * cnt * n3), vs(nsamp * cnt * n3);
+      if (int r = nbg_integrate_sampled(k, h, nsteps, stride, grad, xs.data(), vs.data())) return r;
+      for (size_t q = 0; q < nsamp; ++q) {
+        std::memcpy(x_samples + (q * B + lo) * n3, xs.data() + q * cnt * n3, cnt * n3 * 8);
+        std::memcpy(v_samples + (q * B + lo) * n3, vs.data() + q * cnt * n3, cnt * n3 * 8);
+      }
+      return 0;
+    });
+  }
+  if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
   CK(cudaSetDevice(p->device));
+  p->generation++;
   const size_t n = p->n, nsys = p->nsys, ld = p->ld;
   const long nsamp = (long)((nsteps + stride - 1) / stride);
   DevBuf sx, sv, ox;
@@ -1567,16 +1899,14 @@ int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t str
   CK(cudaMemcpy(&t0, p->bt.p, 8, cudaMemcpyDeviceToHost));
   if (grad) if (int r = make_jac_identity(p)) { sx.release(); sv.release(); ox.release(); return r; }
   p->T.samp_x = sx.as<double>(); p->T.samp_v = sv.as<double>(); p->T.samp_stride = (long)stride;
-  Timer tm{p->stream};
-  EventPair ev;
-  cudaEvent_t e0 = ev.a, e1 = ev.b;
-  cudaEventRecord(e0, p->stream);
+  Timer tm(p);
+  tm.start();
   // s.t[1] = t0 + h i (Outputs.jl:43): same time bookkeeping as the transit driver
   const int rc = run_steps(p, h, (long)nsteps, grad != 0, false, 0, t0, h, false, tm, 0.0);
   p->T.samp_x = nullptr; p->T.samp_v = nullptr;
-  cudaEventRecord(e1, p->stream);
+  tm.stop();
   cudaStreamSynchronize(p->stream);
-  finish_timings(p, tm, ev);
+  finish_timings(p, tm);
   if (rc) { sx.release(); sv.release(); ox.release(); return rc; }
   const dim3 grid((unsigned)((nsys + 127) / 128), (unsigned)nsamp);
   double* outs[2] = {x_samples, v_samples};
@@ -1597,20 +1927,32 @@ int32_t nbg_integrate(nbg_plan* p, const double* x0, const double* v0, const dou
                       double h_last, int32_t grad, double* x, double* v, double* xerror, double* verror, double* jac_step, double* jac_error,
                       double* dqdt, uint32_t* status) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) {  // every slice runs its whole upload / integrate / download sequence on its own thread
+    if (!x0 || !v0 || !m) return fail(NBG_ERR_ARG, "plan, x, v, m are required");
+    const size_t n = p->n, M = 7 * n;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_integrate(k, x0 + lo * 3 * n, v0 + lo * 3 * n, m + lo * n, pair, t0, h, nsteps, h_last, grad, at(x, lo * 3 * n), at(v, lo * 3 * n),
+                           at(xerror, lo * 3 * n), at(verror, lo * 3 * n), at(jac_step, lo * M * M), at(jac_error, lo * M * M), at(dqdt, lo * M),
+                           at(status, lo));
+    });
+  }
   if (int r = nbg_set_pair(p, pair)) return r;
   if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
   if (int r = nbg_integrate_resident(p, h, nsteps, h_last, grad, 0, 0.0)) return r;
   return nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, nullptr, status);
 }
 
-int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad,
-                                    const double* jac_init) {
-  if (!p || !p->has_state) return fail(NBG_ERR_ARG, "no state set");
+// Shared body of the transit drivers.  out_mode 0: dense device arrays (nbg_transit_fetch / nbg_transit_chi2 read them afterwards);
+// 1: per-chunk rows streamed to p->sink; 2: fused chi^2 (p->btobs / bsigma / bchi2 / bgq prepared by the caller).
+static int transit_run(nbg_plan* p, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad, const double* jac_init,
+                       int out_mode) {
+  if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
   if (!ntt_body) return fail(NBG_ERR_ARG, "ntt_body is required");
   if (ti < 0 || ti >= p->n) return fail(NBG_ERR_ARG, "ti out of range");
   if (mode != 0 && mode != 1) return fail(NBG_ERR_ARG, "mode must be 0 (TransitTiming) or 1 (TransitParameters)");
   if (h == 0.0) return fail(NBG_ERR_ARG, "h must be non-zero");
   CK(cudaSetDevice(p->device));
+  p->generation++;
   const int n = p->n;
   const size_t nsys = p->nsys, M = 7 * n;
   int RT = 0;
@@ -1620,11 +1962,17 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   }
   p->RT = RT; p->C = mode == 1 ? 3 : 1;
   const size_t C = p->C;
-  if (p->btt.ensure(std::max<size_t>(8, nsys * RT * C * 8))) return fail(NBG_ERR_NOMEM, "tt allocation failed");
-  CK(cudaMemsetAsync(p->btt.p, 0, nsys * RT * C * 8, p->stream));
+  const bool dense = out_mode == 0;
+  if (dense || (out_mode == 2 && p->fused_tt)) {
+    if (p->btt.ensure(std::max<size_t>(8, nsys * RT * C * 8))) return fail(NBG_ERR_NOMEM, "tt allocation failed");
+    CK(cudaMemsetAsync(p->btt.p, 0, nsys * RT * C * 8, p->stream));
+  }
   if (grad) {
-    if (p->bdtdq0.ensure(std::max<size_t>(8, nsys * RT * M * C * 8))) return fail(NBG_ERR_NOMEM, "dtdq0 allocation failed (reduce ntt_body or the batch)");
-    CK(cudaMemsetAsync(p->bdtdq0.p, 0, nsys * RT * M * C * 8, p->stream));
+    if (dense) {
+      if (p->bdtdq0.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
+        return fail(NBG_ERR_NOMEM, "dtdq0 does not fit on the device as a dense array: use nbg_transit_timing (streams rows to host buffers) or nbg_transit_chi2_fused");
+      CK(cudaMemsetAsync(p->bdtdq0.p, 0, nsys * RT * M * C * 8, p->stream));
+    }
     if (int r = make_jac_identity(p)) return r;
   }
   CK(cudaMemcpyAsync(p->bntt.p, p->ntt_body, n * 4, cudaMemcpyHostToDevice, p->stream));
@@ -1635,38 +1983,38 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
   CK(cudaStreamSynchronize(p->stream));
   const long nsteps = std::labs((long)std::nearbyint(tmax / h));         // Transits.jl:143
   const double hs = h * check_step(t0, tmax + t0);                       // Transits.jl:144
-  Timer tm{p->stream};
-  EventPair ev;
-  cudaEvent_t e0 = ev.a, e1 = ev.b;
-  cudaEventRecord(e0, p->stream);
+  Timer tm(p);
+  tm.start();
   const int tpb = 128;
   gsave_init_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T, n, (long)nsys, ti);
   p->launches++;
   // jac_init (M^2 doubles per system, the bulk of the input bytes) is uploaded on a second stream while the steps run
-  const bool want_dtde = grad && (jac_init || p->jinit_resident);
+  const bool want_dtde = out_mode != 2 && grad && (jac_init || p->jinit_resident);
   if (want_dtde) {
-    if ((jac_init && p->bjinit.ensure(nsys * M * M * 8)) || p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8)))
-      return fail(NBG_ERR_NOMEM, "dtdelements allocation failed");
+    if (jac_init && p->bjinit.ensure(nsys * M * M * 8)) return fail(NBG_ERR_NOMEM, "jac_init allocation failed");
+    if (dense && p->bdtde.ensure(std::max<size_t>(8, nsys * RT * M * C * 8))) return fail(NBG_ERR_NOMEM, "dtdelements allocation failed");
     if (jac_init) {
       CK(cudaMemcpyAsync(p->bjinit.p, jac_init, nsys * M * M * 8, cudaMemcpyHostToDevice, p->copy_stream));
       p->jinit_resident = false;
     }  // else: the ics_kernel launched by nbg_set_state_elements on the copy stream produces it
-    CK(cudaMemsetAsync(p->bdtde.p, 0, nsys * RT * M * C * 8, p->copy_stream));
+    if (dense) CK(cudaMemsetAsync(p->bdtde.p, 0, nsys * RT * M * C * 8, p->copy_stream));
     CK(cudaEventRecord(p->copy_done, p->copy_stream));
   }
-  double rate = nsteps > 0 ? (double)RT / (double)nsteps : 1.0;
+  const double rate = nsteps > 0 ? (double)RT / (double)nsteps : 1.0;
   p->sink.want_dtde = want_dtde;
-  p->sink.delivered = false;
-  const double wr0 = wall_ms();
-  if (int r = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate)) { cudaStreamSynchronize(p->copy_stream); return r; }
-  p->have_transit = true;
+  p->sink.active = out_mode == 1;
+  p->fused = out_mode == 2;
   p->transit_grad = grad != 0;
+  p->jobs.clear();
+  p->chunk_seq = 0;
+  const double wr0 = wall_ms();
+  const int rr = run_steps(p, hs, nsteps, grad != 0, true, ti, t0, h, false, tm, rate);
+  p->sink.active = false;
+  p->fused = false;
+  if (rr) { cudaStreamSynchronize(p->copy_stream); cudaStreamSynchronize(p->stream); p->jobs.clear(); return rr; }
+  p->have_transit = dense;
   p->have_dtde = false;
-  if (p->sink.delivered) {  // dtdelements and the output copies ran slice by slice on the copy stream (deliver_slice)
-    CK(cudaEventRecord(p->copy_done, p->copy_stream));
-    CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
-    p->have_dtde = want_dtde;
-  } else if (want_dtde) {
+  if (dense && want_dtde) {
     CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
     CK(cudaFuncSetAttribute(dtdelements_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(M * (M | 1) * 8)));
     dtdelements_kernel<<<(unsigned)nsys, 256, M * (M | 1) * 8, p->stream>>>(p->bdtdq0.as<double>(), p->bjinit.as<double>(), p->bdtde.as<double>(),
@@ -1675,22 +2023,42 @@ int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t 
     p->launches++;
     p->have_dtde = true;
   }
-  cudaEventRecord(e1, p->stream);
+  tm.stop();
   const double wr1 = wall_ms();
   CK(cudaStreamSynchronize(p->stream));
+  CK(cudaStreamSynchronize(p->copy_stream));
   const double wr2 = wall_ms();
-  finish_timings(p, tm, ev);
-  if (p->trace) fprintf(stderr, "[nbg trace] resident: launches issued in %.2f ms, then waited %.2f ms, timing readback %.2f ms\n", wr1 - wr0, wr2 - wr1, wall_ms() - wr2);
+  finish_timings(p, tm);
+  if (p->trace) fprintf(stderr, "[nbg trace] transit run: host loop %.2f ms, then waited %.2f ms, timing readback %.2f ms, chunk re-runs so far %ld\n", wr1 - wr0, wr2 - wr1, wall_ms() - wr2, p->chunk_retries);
   CK(cudaGetLastError());
   return NBG_OK;
 }
 
+int32_t nbg_transit_timing_resident(nbg_plan* p, double h, double tmax, int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad,
+                                    const double* jac_init) {
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) {
+    const size_t M = 7 * (size_t)p->n;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) { return nbg_transit_timing_resident(k, h, tmax, ti, ntt_body, mode, grad, at(jac_init, lo * M * M)); });
+  }
+  return transit_run(p, h, tmax, ti, ntt_body, mode, grad, jac_init, 0);
+}
+
 int32_t nbg_transit_fetch(nbg_plan* p, double* tt, int64_t* count, double* dtdq0, double* dtdelements) {
-  if (!p || !p->have_transit) return fail(NBG_ERR_ARG, "no transit results");
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) {
+    const nbg_plan* k0 = p->kids[0];
+    const size_t M = 7 * (size_t)p->n, C = k0->C, RT = k0->RT;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_transit_fetch(k, at(tt, lo * RT * C), at(count, (size_t)lo * p->n), at(dtdq0, lo * RT * M * C), at(dtdelements, lo * RT * M * C));
+    });
+  }
   CK(cudaSetDevice(p->device));
   const size_t nsys = p->nsys, M = 7 * p->n, C = p->C, RT = p->RT;
+  if ((tt || dtdq0 || dtdelements) && !p->have_transit) return fail(NBG_ERR_ARG, "no dense transit results (run nbg_transit_timing_resident first)");
   if (tt) CK(cudaMemcpyAsync(tt, p->btt.p, nsys * RT * C * 8, cudaMemcpyDeviceToHost, p->stream));
   if (count) {
+    if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
     if (p->stage[7].ensure(nsys * p->n * 8)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
     const int tpb = 128;
     count_out_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->bcount.as<int32_t>(), p->ld, p->n, (long)nsys, p->stage[7].as<int64_t>());
@@ -1705,8 +2073,16 @@ int32_t nbg_transit_fetch(nbg_plan* p, double* tt, int64_t* count, double* dtdq0
 
 int32_t nbg_transit_chi2(nbg_plan* p, const double* t_obs, const double* sigma, int32_t per_system, double* chi2, double* grad_q0,
                          double* grad_elements) {
-  if (!p || !p->have_transit) return fail(NBG_ERR_ARG, "no transit results");
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
   if (!t_obs || !sigma || !chi2) return fail(NBG_ERR_ARG, "t_obs, sigma and chi2 are required");
+  if (!p->kids.empty()) {
+    const size_t M = 7 * (size_t)p->n, RT = p->kids[0]->RT;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_transit_chi2(k, per_system ? t_obs + lo * RT : t_obs, per_system ? sigma + lo * RT : sigma, per_system, chi2 + lo, at(grad_q0, lo * M),
+                              at(grad_elements, lo * M));
+    });
+  }
+  if (!p->have_transit) return fail(NBG_ERR_ARG, "no dense transit results (run nbg_transit_timing_resident first)");
   if (p->C != 1) return fail(NBG_ERR_UNSUPPORTED, "chi^2 is defined for TransitTiming (mode 0) results");
   if (grad_q0 && !p->transit_grad) return fail(NBG_ERR_ARG, "the last transit call ran with grad = 0");
   if (grad_elements && !p->have_dtde) return fail(NBG_ERR_ARG, "no dtdelements (jac_init was not given)");
@@ -1732,34 +2108,106 @@ int32_t nbg_transit_chi2(nbg_plan* p, const double* t_obs, const double* sigma, 
   return NBG_OK;
 }
 
+// Fused transit-time likelihood (SURVEY 8(f) f2 as specified): the whole transit-timing run from the resident state with chi^2 and its
+// gradient accumulated where dt/dq0 is produced (the transit branch of the Jacobian kernel); no dtdq0 / dtdelements row is ever stored.
+int32_t nbg_transit_chi2_fused(nbg_plan* p, double h, double tmax, int32_t ti, const int32_t* ntt_body, const double* t_obs, const double* sigma,
+                               int32_t per_system, int32_t seed_jac_init, int32_t grad, double* chi2, double* grad_out, int64_t* count, double* tt) {
+  if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!t_obs || !sigma || !chi2 || !ntt_body) return fail(NBG_ERR_ARG, "ntt_body, t_obs, sigma and chi2 are required");
+  if (grad && !grad_out) return fail(NBG_ERR_ARG, "grad_out is required with grad = 1");
+  if (!p->kids.empty()) {
+    size_t RT = 0;
+    for (int i = 0; i < p->n; ++i) RT += (size_t)std::max(0, ntt_body[i]);
+    const size_t M = 7 * (size_t)p->n;
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_transit_chi2_fused(k, h, tmax, ti, ntt_body, per_system ? t_obs + lo * RT : t_obs, per_system ? sigma + lo * RT : sigma, per_system,
+                                    seed_jac_init, grad, chi2 + lo, at(grad_out, lo * M), at(count, (size_t)lo * p->n), at(tt, lo * RT));
+    });
+  }
+  if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  CK(cudaSetDevice(p->device));
+  const size_t nsys = p->nsys, n = p->n, M = 7 * n;
+  size_t RT = 0;
+  for (size_t i = 0; i < n; ++i) RT += (size_t)std::max(0, ntt_body[i]);
+  const size_t nobs = (per_system ? nsys : 1) * RT;
+  if (p->btobs.ensure(std::max<size_t>(8, nobs * 8)) || p->bsigma.ensure(std::max<size_t>(8, nobs * 8)) || p->bchi2.ensure(nsys * 8) ||
+      p->bgq.ensure(nsys * M * 8))
+    return fail(NBG_ERR_NOMEM, "chi^2 buffers allocation failed");
+  CK(cudaMemcpyAsync(p->btobs.p, t_obs, nobs * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemcpyAsync(p->bsigma.p, sigma, nobs * 8, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaMemsetAsync(p->bchi2.p, 0, nsys * 8, p->stream));
+  CK(cudaMemsetAsync(p->bgq.p, 0, nsys * M * 8, p->stream));
+  if (grad && seed_jac_init) {
+    // jac_step = jac_init instead of the identity: every row the Jacobian kernel forms is then a derivative with respect to the
+    // orbital elements, so the accumulated gradient is d chi2 / d elements with no dtdelements pass
+    if (!p->jinit_resident) return fail(NBG_ERR_ARG, "seed_jac_init needs the device-computed jac_init (nbg_set_state_elements with want_jac_init)");
+    if (int r = ensure_jac(p)) return r;
+    CK(cudaStreamWaitEvent(p->stream, p->copy_done, 0));
+    jac_from_julia_kernel<<<(unsigned)nsys, 256, 0, p->stream>>>(p->bjinit.as<double>(), p->bJv.as<double>(), (int)n, 0);
+    jac_from_julia_kernel<<<(unsigned)nsys, 256, 0, p->stream>>>(nullptr, p->bJe.as<double>(), (int)n, 1);
+    p->launches += 2;
+    p->jac_valid = true;
+  }
+  p->fused_per_system = per_system ? 1 : 0;
+  p->fused_tt = tt != nullptr;
+  if (int r = transit_run(p, h, tmax, ti, ntt_body, 0, grad, nullptr, 2)) return r;
+  CK(cudaMemcpyAsync(chi2, p->bchi2.p, nsys * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (grad) CK(cudaMemcpyAsync(grad_out, p->bgq.p, nsys * M * 8, cudaMemcpyDeviceToHost, p->stream));
+  if (tt) CK(cudaMemcpyAsync(tt, p->btt.p, nsys * RT * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (count) return nbg_transit_fetch(p, nullptr, count, nullptr, nullptr);
+  return NBG_OK;
+}
+
 int32_t nbg_transit_timing(nbg_plan* p, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0, double h, double tmax,
                            int32_t ti, const int32_t* ntt_body, int32_t mode, int32_t grad, const double* jac_init, double* tt, int64_t* count,
                            double* dtdq0, double* dtdelements, double* x, double* v, double* xerror, double* verror, double* jac_step,
                            double* jac_error, double* dqdt, double* t, uint32_t* status) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
+  if (!p->kids.empty()) {  // every slice runs the whole one-shot sequence on its own thread: uploads, steps and output streaming of the devices overlap
+    if (!x0 || !v0 || !m || !ntt_body) return fail(NBG_ERR_ARG, "x, v, m and ntt_body are required");
+    const size_t n = p->n, M = 7 * n, C = mode == 1 ? 3 : 1;
+    size_t RT = 0;
+    for (size_t i = 0; i < n; ++i) RT += (size_t)std::max(0, ntt_body[i]);
+    return for_kids(p, [&](nbg_plan* k, long lo, long) {
+      return nbg_transit_timing(k, x0 + lo * 3 * n, v0 + lo * 3 * n, m + lo * n, pair, t0, h, tmax, ti, ntt_body, mode, grad, at(jac_init, lo * M * M),
+                                at(tt, lo * RT * C), at(count, lo * n), at(dtdq0, lo * RT * M * C), at(dtdelements, lo * RT * M * C), at(x, lo * 3 * n),
+                                at(v, lo * 3 * n), at(xerror, lo * 3 * n), at(verror, lo * 3 * n), at(jac_step, lo * M * M), at(jac_error, lo * M * M),
+                                at(dqdt, lo * M), at(t, lo), at(status, lo));
+    });
+  }
   const double w0 = wall_ms();
   if (int r = nbg_set_pair(p, pair)) return r;
   if (int r = nbg_set_state(p, x0, v0, m, t0, nullptr, nullptr, nullptr, nullptr, nullptr)) return r;
   const double w1 = wall_ms();
-  // the host destinations are known before the run: let the last chunk stream its outputs slice by slice (OutSink)
-  const bool sliced = grad && p->out_slices > 1 && p->nsys >= p->out_slice_min && p->kmask == 0u && p->n <= NBG_RX_MAX_BODIES && !p->force_generic_jac;
-  p->sink = nbg_plan::OutSink{tt, dtdq0, dtdelements, sliced ? p->out_slices : 0, false, false};
-  const int rr = nbg_transit_timing_resident(p, h, tmax, ti, ntt_body, mode, grad, jac_init);
-  const bool delivered = p->sink.delivered;
-  p->sink = nbg_plan::OutSink{};
+  // The host destinations are known before the run: every chunk's transit rows (tt, dtdq0, dtdelements) are copied to pinned staging on
+  // the copy stream and scattered into the caller's arrays while the following chunks compute, so the device never holds more than
+  // one chunk of outputs -- the full-length BASELINE configuration (2 x 83 GB of gradients at 65,536 systems) runs in one call.
+  p->sink = nbg_plan::Sink{tt, grad ? dtdq0 : nullptr, grad ? dtdelements : nullptr, false, false};
+  const int rr = transit_run(p, h, tmax, ti, ntt_body, mode, grad, jac_init, 1);
+  p->sink = nbg_plan::Sink{};
   if (rr) return rr;
   const double w2 = wall_ms();
-  if (int r = nbg_transit_fetch(p, delivered ? nullptr : tt, count, delivered ? nullptr : dtdq0, delivered ? nullptr : dtdelements)) return r;
+  if (count) if (int r = nbg_transit_fetch(p, nullptr, count, nullptr, nullptr)) return r;
   const double w3 = wall_ms();
   const int rg = nbg_get_state(p, x, v, xerror, verror, grad ? jac_step : nullptr, grad ? jac_error : nullptr, grad ? dqdt : nullptr, t, status);
   if (p->trace)
-    fprintf(stderr, "[nbg trace] transit_timing: set_state %.2f ms, resident %.2f ms (device total %.2f), fetch %.2f ms, get_state %.2f ms\n", w1 - w0,
+    fprintf(stderr, "[nbg trace] transit_timing: set_state %.2f ms, run %.2f ms (device total %.2f), count %.2f ms, get_state %.2f ms\n", w1 - w0,
             w2 - w1, p->timings[4], w3 - w2, wall_ms() - w3);
   return rg;
 }
 
 int32_t nbg_counters(nbg_plan* p, int64_t* c8) {
   if (!p || !c8) return fail(NBG_ERR_ARG, "NULL argument");
+  if (!p->kids.empty()) {
+    for (int q = 0; q < 8; ++q) c8[q] = 0;
+    for (nbg_plan* k : p->kids) {
+      int64_t c[8];
+      nbg_counters(k, c);
+      for (int q = 0; q < 8; ++q) c8[q] = q == 6 ? std::max(c8[q], c[q]) : c8[q] + c[q];
+    }
+    return NBG_OK;
+  }
   for (int q = 0; q < 8; ++q) c8[q] = (int64_t)p->counters_host[q];
   c8[4] = p->launches;
   c8[5] = (int64_t)(p->counters_host[5] + p->counters_host[4]);
@@ -1767,42 +2215,73 @@ int32_t nbg_counters(nbg_plan* p, int64_t* c8) {
 }
 int32_t nbg_counters_reset(nbg_plan* p) {
   if (!p) return fail(NBG_ERR_ARG, "NULL argument");
+  if (!p->kids.empty()) {
+    for (nbg_plan* k : p->kids) if (int r = nbg_counters_reset(k)) return r;
+    return NBG_OK;
+  }
   CK(cudaSetDevice(p->device));
   for (auto& q : p->counters_host) q = 0;
   p->launches = 0;
+  p->chunk_retries = 0;
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   CK(cudaStreamSynchronize(p->stream));
   return NBG_OK;
 }
 int32_t nbg_last_timings(nbg_plan* p, double* ms8) {
   if (!p || !ms8) return fail(NBG_ERR_ARG, "NULL argument");
+  if (!p->kids.empty()) {  // slices run concurrently: the slowest slice is the call
+    for (int q = 0; q < 8; ++q) ms8[q] = 0;
+    for (nbg_plan* k : p->kids) for (int q = 0; q < 8; ++q) ms8[q] = std::max(ms8[q], k->timings[q]);
+    return NBG_OK;
+  }
   for (int q = 0; q < 8; ++q) ms8[q] = p->timings[q];
   return NBG_OK;
 }
-int64_t nbg_cuda_stream(nbg_plan* p) { return p ? (int64_t)(intptr_t)p->stream : 0; }
+int64_t nbg_cuda_stream(nbg_plan* p) { return !p ? 0 : (int64_t)(intptr_t)(p->kids.empty() ? p->stream : p->kids[0]->stream); }
+int64_t nbg_chunk_retries(nbg_plan* p) {
+  if (!p) return 0;
+  long r = p->chunk_retries;
+  for (nbg_plan* k : p->kids) r += k->chunk_retries;
+  return r;
+}
+int64_t nbg_state_generation(nbg_plan* p) {
+  if (!p) return 0;
+  int64_t g = p->generation;
+  for (nbg_plan* k : p->kids) g += k->generation;
+  return g;
+}
+int32_t nbg_plan_devices(nbg_plan* p, int32_t* devices, int32_t cap) {
+  if (!p) return 0;
+  if (p->kids.empty()) { if (devices && cap > 0) devices[0] = p->device; return 1; }
+  for (size_t k = 0; k < p->kids.size() && (int)k < cap; ++k) if (devices) devices[k] = p->kids[k]->device;
+  return (int32_t)p->kids.size();
+}
 
 int32_t nbg_fp64_peak(int32_t device, double* tflops, double* ms) {
-  if (nbg_device_count() == 0) return fail(NBG_ERR_NO_DEVICE, "no CUDA device: libnbgrad_b200 has no CPU fallback");
+  const int ndev = nbg_device_count();
+  if (ndev == 0) return fail(NBG_ERR_NO_DEVICE, "no CUDA device: libnbgrad_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(NBG_ERR_ARG, "device index out of range");
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
-  double* out = nullptr;
-  CK(cudaMalloc(&out, (size_t)blocks * threads * 8));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  struct Res {  // released on every exit path
+    double* out = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Res() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (out) cudaFree(out); }
+  } R;
+  CK(cudaMalloc(&R.out, (size_t)blocks * threads * 8));
+  CK(cudaEventCreate(&R.e0));
+  CK(cudaEventCreate(&R.e1));
   float best = 1e30f;
   for (int rep = 0; rep < 6; ++rep) {
-    cudaEventRecord(e0);
-    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
-    cudaEventRecord(e1);
-    CK(cudaEventSynchronize(e1));
+    CK(cudaEventRecord(R.e0));
+    dfma_peak_kernel<<<blocks, threads>>>(R.out, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(R.e1));
+    CK(cudaEventSynchronize(R.e1));
     float t = 0;
-    cudaEventElapsedTime(&t, e0, e1);
+    CK(cudaEventElapsedTime(&t, R.e0, R.e1));
     if (rep > 0 && t < best) best = t;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(out);
   const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
   if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
   if (ms) *ms = best;

@@ -12,7 +12,8 @@ ST_NONFINITE, ST_TRANSIT_ITMAX, ST_EVENT_OVERFLOW, ST_NTT_OVERFLOW = 1, 2, 4, 8
 # every symbol include/nbgrad.h declares
 SYMBOLS = ["nbg_version", "nbg_last_error", "nbg_device_count", "nbg_plan_create", "nbg_plan_destroy", "nbg_set_pair", "nbg_set_state", "nbg_set_state_elements", "nbg_get_jac_init", "nbg_get_state",
            "nbg_integrate_resident", "nbg_integrate_sampled", "nbg_integrate", "nbg_transit_timing_resident", "nbg_transit_fetch", "nbg_transit_chi2", "nbg_transit_timing",
-           "nbg_counters", "nbg_counters_reset", "nbg_last_timings", "nbg_cuda_stream", "nbg_fp64_peak"]
+           "nbg_counters", "nbg_counters_reset", "nbg_last_timings", "nbg_cuda_stream", "nbg_fp64_peak", "nbg_build_flags", "nbg_plan_create_multi", "nbg_plan_devices",
+           "nbg_state_generation", "nbg_transit_chi2_fused", "nbg_chunk_retries"]
 
 
 class NbgError(RuntimeError):
@@ -28,10 +29,12 @@ def lib():
         if not os.path.exists(LIB):
             raise NbgError("libnbgrad_b200.so is not built (%s): run `python __graft_entry__.py build`; there is no CPU fallback" % LIB)
         L = C.CDLL(LIB)
-        L.nbg_last_error.restype = C.c_char_p
-        L.nbg_cuda_stream.restype = C.c_int64
         for s in SYMBOLS:
             getattr(L, s)
+        L.nbg_last_error.restype = C.c_char_p
+        L.nbg_cuda_stream.restype = C.c_int64
+        L.nbg_chunk_retries.restype = C.c_int64
+        L.nbg_state_generation.restype = C.c_int64
         _lib = L
     return _lib
 

@@ -6,15 +6,25 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.environ.get("NBGRAD_B200_LIB") or os.path.join(CSRC, "libnbgrad_b200.so")  # env override: A/B builds on the GPU box
 SOURCES = ["nbg_b200.cu"]
-HEADERS = ["nbg_kepler.cuh", "nbg_step.cuh", "nbg_jacobian.cuh", os.path.join("..", "..", "include", "nbgrad.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+# NBGRAD_EXPERIMENTS=1 also compiles the measured-and-rejected kernel variants (DMMA Jacobian kernel, pivot-block / lockstep variants of
+# jac_rx_kernel: DESIGN.md 5); they double the build time and are off by default
+if os.environ.get("NBGRAD_EXPERIMENTS") == "1":
+    NVCC_FLAGS.append("-DNBG_EXPERIMENTS")
+
+
+def dependencies():
+    """Everything the library is compiled from: every .cu / .cuh / .inc in csrc/ and the public header."""
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inc"))]
+    deps.append(os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "nbgrad.h"))
+    return deps
 
 
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in dependencies())
 
 
 def build(force=False, verbose=False):

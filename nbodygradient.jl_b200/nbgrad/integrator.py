@@ -26,22 +26,47 @@ def ahl21(*_a, **_k):
     raise _lib.NbgError("ahl21 is executed on the device through Integrator(...)")
 
 
-_plans = {}
+import atexit
+from collections import OrderedDict
+
+_plans = OrderedDict()   # (n, nsys, devices, stream_budget) -> plan; least recently used first
+MAX_PLANS = 4            # a plan keeps its device buffers (operator streams: up to 1/4 of the free memory): callers that vary the batch
+                         # shape must not accumulate them
+
+
+def _devices(device):
+    """device=: an int (one GPU) or a sequence of ints (nbg_plan_create_multi: the batch is cut into one contiguous slice per entry)."""
+    if isinstance(device, (int, np.integer)):
+        return (int(device),)
+    return tuple(int(d) for d in device)
 
 
 def _plan(n, nsys, device=0, stream_budget=0):
-    key = (n, nsys, device, stream_budget)
-    if key not in _plans:
-        p = C.c_void_p()
-        check(_lib.lib().nbg_plan_create(C.byref(p), C.c_int32(n), C.c_int64(nsys), C.c_int32(device), C.c_int64(stream_budget)))
-        _plans[key] = p
-    return _plans[key]
+    devs = _devices(device)
+    key = (n, nsys, devs, stream_budget)
+    if key in _plans:
+        _plans.move_to_end(key)
+        return _plans[key]
+    while len(_plans) >= MAX_PLANS:
+        _, old = _plans.popitem(last=False)
+        _lib.lib().nbg_plan_destroy(old)
+    p = C.c_void_p()
+    if len(devs) == 1:
+        check(_lib.lib().nbg_plan_create(C.byref(p), C.c_int32(n), C.c_int64(nsys), C.c_int32(devs[0]), C.c_int64(stream_budget)))
+    else:
+        d = np.asarray(devs, dtype=np.int32)
+        check(_lib.lib().nbg_plan_create_multi(C.byref(p), C.c_int32(n), C.c_int64(nsys), ptr(d), C.c_int32(len(devs)), C.c_int64(stream_budget)))
+    _plans[key] = p
+    return p
 
 
 def release_plans():
     for p in _plans.values():
         _lib.lib().nbg_plan_destroy(p)
     _plans.clear()
+
+
+atexit.register(release_plans)
 
 
 def check_step(t0, tmax):
@@ -61,6 +86,7 @@ class State:
         """on_device=True: init_nbody (elements -> x, v, jac_init) runs in libnbgrad_b200 (nbg_set_state_elements) instead of
         the numpy IC layer; the state stays resident, so the next Integrator call skips the upload of x, v, m and jac_init."""
         self._resident_plan = None
+        self._resident_copy = None
         if on_device:
             if not hasattr(ic, "elements"):
                 raise TypeError("State(ic, on_device=True) needs an ElementsIC")
@@ -90,6 +116,7 @@ class State:
         B, n = ic.elements.shape[0], ic.nbody
         M = 7 * n
         plan = _plan(n, B, device, 0)
+        self._resident_t0 = float(ic.t0)
         el = ic.elements.copy()
         el[:, :, 0] = ic.m                                               # masses live in ic.m (as in ic.init_nbody)
         el = np.ascontiguousarray(el.transpose(0, 2, 1))                # [sys][c][i] = Julia elements[i,c], system slowest
@@ -102,14 +129,19 @@ class State:
             jcm = np.empty((B, M, M))
             check(L.nbg_get_jac_init(plan, ptr(jcm)))
             jac_init = jcm.transpose(0, 2, 1).copy()
-        self._resident_plan = plan   # the device already holds this state: the first Integrator call on it skips the upload
-        self._resident_sig = (float(x.sum()), float(v.sum()), float(ic.m.sum()))
+        # The device already holds this state: the first Integrator call on it skips the upload -- but only if the plan (shared by every
+        # State / Integrator of this shape) has not been given another state or stepped since: nbg_state_generation is bumped by every
+        # call that changes the resident state, and the host copies are compared bit for bit (the arrays are public and may be edited).
+        self._resident_plan = plan
+        self._resident_gen = int(L.nbg_state_generation(plan))
+        self._resident_copy = (x.copy(), v.copy(), np.array(ic.m, dtype=np.float64), None if jac_init is None else jac_init.copy())
         return x, v, jac_init
 
     def copy(self):
         import copy
         s = copy.copy(self)
         s._resident_plan = None
+        s._resident_copy = None
         for k, val in self.__dict__.items():
             if isinstance(val, np.ndarray) and k != "m":
                 setattr(s, k, val.copy())
@@ -124,10 +156,14 @@ class State:
         """Returns True if the state (and jac_init) was already resident from State(ic, on_device=True)."""
         L = _lib.lib()
         if self._resident_plan is not None:
-            # still the state the device computed?  (the arrays are public: a caller may have edited them, e.g. tilt)
-            fresh = (self._resident_plan.value == plan.value and not self.jac_error.any() and not self.xerror.any() and
-                     self._resident_sig == (float(self.x.sum()), float(self.v.sum()), float(np.asarray(self.m).sum())))
+            # still the state the device computed, and still the one the plan holds?
+            cx, cv, cm, cj = self._resident_copy
+            fresh = (self._resident_plan.value == plan.value and int(L.nbg_state_generation(plan)) == self._resident_gen and self._fresh
+                     and not self.jac_error.any() and not self.xerror.any() and not self.verror.any() and not self.dqdt.any()
+                     and np.array_equal(self.x, cx) and np.array_equal(self.v, cv) and np.array_equal(np.asarray(self.m), cm)
+                     and (cj is None or np.array_equal(self.jac_init, cj)) and float(self.t[0]) == self._resident_t0)
             self._resident_plan = None
+            self._resident_copy = None
             if fresh:
                 pr = np.asfortranarray(self.pair.astype(np.uint8))
                 check(L.nbg_set_pair(plan, ptr(pr) if pr.any() else None))
@@ -214,7 +250,10 @@ class CartesianOutput:
 class Integrator:
     """Integrator(h, tmax) | Integrator(h, t0, tmax) | Integrator(scheme, h, t0, tmax) — Integrator.jl:17-31."""
 
-    def __init__(self, *args, device=0, stream_budget=0):
+    def __init__(self, *args, device=0, devices=None, stream_budget=0, keep_dense=False):
+        """device / devices: one CUDA device index, or a list of them -- the batch is then cut into one contiguous slice per entry
+        (nbg_plan_create_multi; one host thread per slice inside the library).  keep_dense: keep tt / dtdq0 / dtdelements of a transit
+        call as dense arrays on the device (needed by chi2(); fails if they do not fit) instead of streaming rows chunk by chunk."""
         if len(args) and callable(args[0]):
             if args[0] is not ahl21:
                 raise _lib.NbgError("NBG_ERR_UNSUPPORTED: only the ahl21 scheme is built")
@@ -227,8 +266,10 @@ class Integrator:
         else:
             raise TypeError("Integrator(h, tmax) | Integrator(h, t0, tmax) | Integrator(scheme, h, t0, tmax)")
         self.scheme, self.h, self.t0, self.tmax = ahl21, float(h), float(t0), float(tmax)
-        self.device, self.stream_budget = device, stream_budget
+        self.device, self.stream_budget, self.keep_dense = (devices if devices is not None else device), stream_budget, keep_dense
         self.last_timings = None
+        self._last_plan = self._last_tt = None
+        self._last_dense = False
 
     def _p(self, s):
         return _plan(s.n, s.nsys, self.device, self.stream_budget)
@@ -303,11 +344,11 @@ class Integrator:
         t_raw = np.zeros(shp_t)
         d_raw = np.zeros(shp_d) if grad else None
         e_raw = np.zeros(shp_d) if want_dtde else None
-        one_shot = (s._fresh and s._resident_plan is None and not s.xerror.any() and not s.verror.any() and not s.dqdt.any()
-                    and not s.jac_error.any())
+        one_shot = (not self.keep_dense and s._fresh and s._resident_plan is None and not s.xerror.any() and not s.verror.any()
+                    and not s.dqdt.any() and not s.jac_error.any())
         if one_shot:
-            # a fresh State(ic): the one-shot entry point knows the host destinations before it starts, so the library copies the
-            # outputs out slice by slice during the last chunk instead of after the last kernel
+            # a fresh State(ic): the one-shot entry point knows the host destinations before it starts, so the library streams every
+            # chunk's transit rows to them while the next chunk computes and never holds the full arrays on the device
             pr = np.asfortranarray(s.pair.astype(np.uint8))
             m_c = np.ascontiguousarray(s.m, dtype=np.float64)
             ji = np.ascontiguousarray(s.jac_init.transpose(0, 2, 1)) if want_dtde else None
@@ -343,12 +384,18 @@ class Integrator:
                 if e_raw is not None:
                     tt.dtbvdelements[...] = e_raw.transpose(0, 5, 1, 2, 4, 3)
         self._timings(plan)
-        self._last_plan, self._last_tt = plan, tt
+        self._last_plan, self._last_tt, self._last_dense = plan, tt, not one_shot
+        st = s.status
+        if (st & _lib.ST_EVENT_OVERFLOW).any():   # cannot happen since v2 (chunks are re-run); never let incomplete results pass silently
+            raise _lib.NbgError("transit queue overflow: results are incomplete")
 
     def chi2(self, t_obs, sigma):
-        """Fused transit-time likelihood on the device for the LAST (s, tt::TransitTiming) call of this Integrator (nbg_transit_chi2):
-        chi2[b] = sum ((tt - t_obs)/sigma)^2 and its gradients w.r.t. the initial Cartesian state [b,q,p] and the elements [b,q,p].
+        """Transit-time likelihood reduced on the device from the dense arrays of the LAST (s, tt::TransitTiming) call of this Integrator
+        (nbg_transit_chi2; needs Integrator(..., keep_dense=True) or a non-fresh State): chi2[b] = sum ((tt - t_obs)/sigma)^2 and its
+        gradients w.r.t. the initial Cartesian state [b,q,p] and the elements [b,q,p].
         t_obs, sigma: [n, ntt] (shared by the batch) or [B, n, ntt]; sigma <= 0 or NaN t_obs = no observation in that slot."""
+        if self._last_plan is None or not self._last_dense:
+            raise _lib.NbgError("chi2() reduces the dense device arrays of the last transit call: use Integrator(..., keep_dense=True), or chi2_fused()")
         plan, tt = self._last_plan, self._last_tt
         B, n, M = tt.nsys, tt.n, 7 * tt.n
         t_obs = np.ascontiguousarray(t_obs, dtype=np.float64); sigma = np.ascontiguousarray(sigma, dtype=np.float64)
@@ -356,6 +403,40 @@ class Integrator:
         chi2, gq, ge = np.zeros(B), np.zeros((B, n, 7)), np.zeros((B, n, 7))
         check(_lib.lib().nbg_transit_chi2(plan, ptr(t_obs), ptr(sigma), C.c_int32(per_system), ptr(chi2), ptr(gq), ptr(ge)))
         return chi2, gq.transpose(0, 2, 1).copy(), ge.transpose(0, 2, 1).copy()
+
+
+def _chi2_fused(self, s, tt, t_obs, sigma, wrt="q0", grad=True, want_tt=False):
+    """The transit-timing run with the likelihood fused into the Jacobian kernel (nbg_transit_chi2_fused): no dtdq0 / dtdelements array
+    exists anywhere, 1 + 7n doubles per system come back.  wrt = "q0": gradient w.r.t. the initial Cartesian state; "elements": w.r.t.
+    the orbital elements -- needs State(ic, on_device=True) (jac_step is seeded with the device-computed jac_init).
+    Returns chi2[b], grad[b,q,p] (None with grad=False); tt.count is filled, tt.tt too if want_tt."""
+    L = _lib.lib()
+    plan = self._p(s)
+    n, B, ntt = s.n, s.nsys, tt.ntt
+    if tt.ncomp != 1:
+        raise _lib.NbgError("NBG_ERR_UNSUPPORTED: chi^2 is defined for TransitTiming")
+    seed = wrt == "elements"
+    resident = s._upload(plan, grad)
+    if seed and not resident:
+        raise _lib.NbgError("wrt='elements' needs a fresh State(ic, on_device=True) (the device-computed jac_init seeds jac_step)")
+    ntt_body = np.full(n, ntt, dtype=np.int32)
+    t_obs = np.ascontiguousarray(t_obs, dtype=np.float64); sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    per_system = 1 if t_obs.ndim == 3 else 0
+    chi2 = np.zeros(B)
+    g = np.zeros((B, n, 7)) if grad else None
+    t_raw = np.zeros((B, n, ntt)) if want_tt else None
+    check(L.nbg_transit_chi2_fused(plan, C.c_double(self.h), C.c_double(self.tmax), C.c_int32(tt.ti), ptr(ntt_body), ptr(t_obs), ptr(sigma),
+                                   C.c_int32(per_system), C.c_int32(1 if seed else 0), C.c_int32(1 if grad else 0), ptr(chi2), ptr(g), ptr(tt.count),
+                                   ptr(t_raw)))
+    if want_tt:
+        tt.tt[...] = t_raw
+    s._download(plan, grad)
+    self._timings(plan)
+    self._last_plan, self._last_tt, self._last_dense = plan, tt, False
+    return chi2, (g.transpose(0, 2, 1).copy() if grad else None)
+
+
+Integrator.chi2_fused = _chi2_fused
 
 
 def device_count():

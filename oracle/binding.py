@@ -177,3 +177,19 @@ class Oracle:
         self.lib.nbgoq_transit_times(C.c_int(n), _ptr(el), C.c_double(t0), C.c_double(h), C.c_double(tmax), C.c_int(ti), C.c_int(ntt), _ptr(tt),
                                      _ptr(count))
         return tt.T.copy(), count
+
+    def quad_transit_timing_grad(self, x, v, m, jac_init, t0, h, tmax, ntt, ti=0):
+        """The full gradient path in __float128 from double inputs (nbgoq_transit_timing_grad); same return layout as transit_timing plus
+        the final x, v, jac_step_cm, all rounded to double."""
+        n = len(m)
+        M = 7 * n
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(n, 3)); v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(n, 3))
+        m = np.ascontiguousarray(m, dtype=np.float64)
+        ji = np.ascontiguousarray(np.asarray(jac_init).T)
+        tt = np.zeros((ntt, n)); count = np.zeros(n, dtype=np.int64)
+        dtdq0 = np.zeros((n, 7, ntt, n)); dtde = np.zeros((n, 7, ntt, n))
+        xo = np.zeros((n, 3)); vo = np.zeros((n, 3)); js = np.zeros((M, M))
+        self.lib.nbgoq_transit_timing_grad(C.c_int(n), _ptr(x), _ptr(v), _ptr(m), _ptr(ji), C.c_double(t0), C.c_double(h), C.c_double(tmax), C.c_int(ti),
+                                           C.c_int(ntt), _ptr(tt), _ptr(count), _ptr(dtdq0), _ptr(dtde), _ptr(xo), _ptr(vo), _ptr(js))
+        return dict(tt=tt.T.copy(), count=count, dtdq0=dtdq0.transpose(3, 2, 1, 0).copy(), dtdelements=dtde.transpose(3, 2, 1, 0).copy(), x=xo, v=vo,
+                    jac_step_cm=js)

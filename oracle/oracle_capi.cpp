@@ -273,4 +273,25 @@ int nbgoq_transit_times(int n, const double* elements, double t0, double h, doub
   return 0;
 }
 
+// quad-precision run of the FULL gradient path (ahl21! with Derivatives, findtransit!, dtbvdq!, calc_dtdelements!) from the same
+// double inputs the double oracle and the GPU get: "the reference algorithm evaluated without round-off".  Used to generate the
+// golden of tests/golden/cfg2_quad_system0.npz (tools/gen_quad_golden.py) against which the full-length test checks that the GPU
+// deviates from the exact map no more than the reference's own Float64 path does.  Outputs are rounded to double.
+int nbgoq_transit_timing_grad(int n, const double* x, const double* v, const double* m, const double* jac_init, double t0, double h, double tmax,
+                              int ti, int ntt, double* tt, long* count, double* dtdq0, double* dtdelements, double* x_out, double* v_out,
+                              double* jac_step) {
+  skip_zero_gemm() = true;
+  State<quad> s = load_state<quad>(n, x, v, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &t0);
+  if (jac_init) for (size_t q = 0; q < (size_t)49 * n * n; ++q) s.jac_init[q] = (quad)jac_init[q];
+  TransitOut<quad> to(n, ntt, ti, 1);
+  integrate_transits(s, to, (quad)h, (quad)tmax, true);
+  for (size_t q = 0; q < to.tt.size(); ++q) tt[q] = (double)to.tt[q];
+  for (int i = 0; i < n; ++i) count[i] = to.count[i];
+  if (dtdq0) for (size_t q = 0; q < to.dtdq0.size(); ++q) dtdq0[q] = (double)to.dtdq0[q];
+  if (dtdelements) for (size_t q = 0; q < to.dtdelements.size(); ++q) dtdelements[q] = (double)to.dtdelements[q];
+  store_state(s, x_out, v_out, nullptr, nullptr, jac_step, nullptr, nullptr, nullptr);
+  skip_zero_gemm() = false;
+  return 0;
+}
+
 }  // extern "C"
