@@ -350,9 +350,10 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   }
 }
 
-// Register-resident Jacobian kernel (N <= NBG_RX_MAX_BODIES = 12): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
-// register budget: 48 + 24 doubles of resident state at N = 8 plus temporaries needs ~230 registers -> 2 blocks of 4 warps per SM;
-// N = 9: 2 blocks of 4 warps at 255 registers; N = 10..12: one block of 5-6 warps per SM (255 registers, 109-163 KB of operator ring)
+// Register-resident Jacobian kernel (N <= NBG_RX_MAX_BODIES = 14): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
+// register budget: 48 + 48 doubles of resident state (jac_step + jac_error halves) at N = 8 plus temporaries needs ~246 registers -> 2 blocks
+// of 4 warps per SM; N = 9: 2 blocks of 4 warps at 255 registers; N = 10: 2 blocks of 5 warps at 168 registers; N = 11..14: one block of 5-7
+// warps per SM (255 registers, 136-219 KB of operator ring)
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
 // SPB systems per block (1 or 2).  With 2, the two systems' warps that share an SM sub-partition run the same straight-line
@@ -993,6 +994,7 @@ struct nbg_plan {
   int phi_cached = 2;  // NBG_PHI_CACHED: 0 = phi_dense_kernel without the shared-memory cache of the per-pair tensors, 1 = T / gam cached, 2 = all pair fields
   int jac_mma = 0;     // NBG_JAC_MMA (NBG_EXPERIMENTS builds only): DMMA Jacobian kernel for N = 8, measured 12-18 % slower than jac_rx_kernel
   int newton_pre = 2;  // gradient-free pre-iterations of the transit Newton solve (NBG_NEWTON_PRE)
+  unsigned scatter_threads = 4;  // NBG_SCATTER_THREADS: host threads that scatter a chunk's transit rows into the caller's arrays
   long queue_cap0 = 0; // NBG_QUEUE_CAP0: initial transit-queue capacity (tests force it tiny to exercise the re-run)
   int32_t ntt_body[NBG_MAX_BODIES] = {0}, off[NBG_MAX_BODIES] = {0};
   int RT = 0, C = 1;
@@ -1116,11 +1118,23 @@ int scatter_job(nbg_plan* p, const nbg_plan::Job& j) {
   const double* tt = (const double*)(base + L.o_tt);
   const double* d = (const double*)(base + L.o_d);
   const double* e = (const double*)(base + L.o_e);
-  for (long q = 0; q < j.nq; ++q) {
-    const size_t rec = (size_t)sys[q] * RT + p->off[body[q]] + k[q];
-    if (p->sink.tt) std::memcpy(p->sink.tt + rec * C, tt + (size_t)q * C, C * 8);
-    if (grad && p->transit_grad) std::memcpy(p->sink.dtdq0 + rec * row, d + (size_t)q * row, row * 8);
-    if (dtde) std::memcpy(p->sink.dtde + rec * row, e + (size_t)q * row, row * 8);
+  auto rows = [&](long q0, long q1) {
+    for (long q = q0; q < q1; ++q) {
+      const size_t rec = (size_t)sys[q] * RT + p->off[body[q]] + k[q];
+      if (p->sink.tt) std::memcpy(p->sink.tt + rec * C, tt + (size_t)q * C, C * 8);
+      if (grad && p->transit_grad) std::memcpy(p->sink.dtdq0 + rec * row, d + (size_t)q * row, row * 8);
+      if (dtde) std::memcpy(p->sink.dtde + rec * row, e + (size_t)q * row, row * 8);
+    }
+  };
+  // rows land in disjoint places: a large chunk (65,536 systems: ~90 k rows, 80 MB) is scattered by a few threads so that the host keeps
+  // up with the device and the last chunks' rows, whose scatter nothing overlaps, cost little
+  const int nth = j.nq >= 16384 ? (int)std::min<unsigned>(p->scatter_threads, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (nth <= 1) {
+    rows(0, j.nq);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t) th.emplace_back(rows, (long)j.nq * t / nth, (long)j.nq * (t + 1) / nth);
+    for (auto& t : th) t.join();
   }
   return 0;
 }
@@ -1553,6 +1567,7 @@ int32_t nbg_plan_create(nbg_plan** out, int32_t nbody, int64_t nsys, int32_t dev
   if (const char* e = getenv("NBG_NEWTON_PRE")) p->newton_pre = std::max(0, std::min(8, atoi(e)));
   if (const char* e = getenv("NBG_TRACE")) p->trace = (e[0] == '1');
   if (const char* e = getenv("NBG_QUEUE_CAP0")) p->queue_cap0 = std::max(0L, atol(e));
+  if (const char* e = getenv("NBG_SCATTER_THREADS")) p->scatter_threads = (unsigned)std::max(1, std::min(64, atoi(e)));
   if (alloc_state(p)) return fail(NBG_ERR_NOMEM, "state allocation failed");
   CK(cudaMemsetAsync(p->bcounters.p, 0, 64, p->stream));
   guard.p = nullptr;

@@ -1,5 +1,5 @@
-// Register-resident Jacobian propagation for N <= 12 bodies (the production path; nbg_jacobian.cuh is the generic
-// shared-memory version used for N = 13..16, where 12 N doubles of resident state per thread no longer fit in 255 registers
+// Register-resident Jacobian propagation for N <= NBG_RX_MAX_BODIES = 14 bodies (the production path; nbg_jacobian.cuh is the generic
+// shared-memory version used for N = 15, 16, where 12 N doubles of resident state per thread no longer fit in 255 registers
 // and a double-buffered operator block no longer fits in 227 KB of shared memory).
 //
 // Why this shape (measured on B200, profiles/microbench/r01_smem_fp64_probe.txt): per SM and per cycle the machine

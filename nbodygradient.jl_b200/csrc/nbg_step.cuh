@@ -8,8 +8,8 @@
 //   drift!/drift_grad!            ahl21_no_grad.jl:24-29, ahl21.jl:318-331
 //   kepler_driftij_gamma!         ahl21.jl:706-760, ahl21_no_grad.jl:192-212
 //   phisalpha!                    ahl21.jl:558-700, ahl21_no_grad.jl:110-158
-// kickfast!/phic! act only on pairs flagged in s.pair, which is all-false unless set by hand
-// (Integrator.jl:91); this build requires pair == all-false (checked at the C ABI).
+// kickfast!/phic! act only on pairs flagged in s.pair, which is all-false unless set by hand (Integrator.jl:91); they live in
+// nbg_kicks.cuh together with ahl21_step, which composes the pieces of this file.
 //
 // Why x, v, dqdt never need the Jacobian: every Jacobian update in the reference is a left
 // multiplication of jac_step by an operator built from x, v, m only, and dqdt obeys the same recurrence

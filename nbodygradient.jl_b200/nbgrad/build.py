@@ -20,6 +20,16 @@ def dependencies():
     return deps
 
 
+def source_hash():
+    """sha1 over the sources the library is compiled from: profiles that quote per-kernel numbers record it, and bench.py refuses to
+    scale a profile taken from other sources."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in dependencies():
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -80,7 +80,7 @@ class Oracle:
         shp_d = (n, 7, ntt, n) if ntbv == 1 else (n, 7, ntt, n, 3)
         tt = np.zeros(shp_tt); count = np.zeros(n, dtype=np.int64)
         dtdq0 = np.zeros(shp_d); dtde = np.zeros(shp_d)
-        stats = np.zeros(3, dtype=np.int64)
+        stats = np.zeros(4, dtype=np.int64)
         ji = None if jac_init is None else np.ascontiguousarray(np.asarray(jac_init).T)  # [row,col] -> column-major
         pair = None if s.get("pair") is None else np.asfortranarray(s["pair"].astype(np.uint8))
         self.lib.nbgo_transit_timing(C.c_int(n), _ptr(s["x"]), _ptr(s["v"]), _ptr(s["m"]), _ptr(pair), _ptr(ji), _ptr(s["t"]), C.c_double(h),
@@ -92,7 +92,7 @@ class Oracle:
             out = dict(tt=tt.T.copy(), dtdq0=dtdq0.transpose(3, 2, 1, 0).copy(), dtdelements=dtde.transpose(3, 2, 1, 0).copy())
         else:
             out = dict(tt=tt.transpose(2, 1, 0).copy(), dtdq0=dtdq0.transpose(4, 3, 2, 1, 0).copy(), dtdelements=dtde.transpose(4, 3, 2, 1, 0).copy())
-        out.update(count=count, newton_iters=int(stats[0]), kepler_calls=int(stats[1]), gamma_iters=int(stats[2]))
+        out.update(count=count, newton_iters=int(stats[0]), kepler_calls=int(stats[1]), gamma_iters=int(stats[2]), itmax_transits=int(stats[3]))
         return out
 
     def batch_transit_timing(self, x, v, m, t0, h, tmax, ntt, ti=0, grad=True, jac_init_cm=None, nthreads=1, want_grad_arrays=True):
@@ -105,10 +105,11 @@ class Oracle:
         dtdq0 = np.zeros((B, n, 7, ntt, n)) if (grad and want_grad_arrays) else None
         dtde = np.zeros((B, n, 7, ntt, n)) if (grad and want_grad_arrays and jac_init_cm is not None) else None
         newton = C.c_long(0)
+        itmax = np.zeros(B, dtype=np.int64)
         self.lib.nbgo_batch_transit_timing(C.c_long(B), C.c_int(n), _ptr(x), _ptr(v), _ptr(m), _ptr(jac_init_cm), C.c_double(t0), C.c_double(h),
                                            C.c_double(tmax), C.c_int(ti), C.c_int(ntt), C.c_int(1 if grad else 0), _ptr(tt), _ptr(count),
-                                           _ptr(dtdq0), _ptr(dtde), C.c_int(nthreads), C.byref(newton))
-        return dict(tt=tt, count=count, dtdq0=dtdq0, dtdelements=dtde, x=x, v=v, newton_iters=newton.value)
+                                           _ptr(dtdq0), _ptr(dtde), C.c_int(nthreads), C.byref(newton), _ptr(itmax))
+        return dict(tt=tt, count=count, dtdq0=dtdq0, dtdelements=dtde, x=x, v=v, newton_iters=newton.value, itmax_per_system=itmax)
 
     def batch_integrate(self, x, v, m, h, nsteps, grad=True, nthreads=1):
         B, n = m.shape

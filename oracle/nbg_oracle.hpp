@@ -1246,6 +1246,7 @@ template <class T> inline void dtbvdq(int i, int j, const State<T>& s, T* out, i
 #undef JS
 }
 
+inline long& itmax_hits() { static thread_local long c = 0; return c; }
 // ---- timing.jl:31-110 findtransit! ------------------------------------------
 // i = transited body (tt.ti), j = occultor.  hstat receives the Newton iteration count.
 template <class T> inline void findtransit(int i, int j, T dt0, State<T>& s, Derivs<T>& d, TransitOut<T>& tt, bool grad, long* newton_iters) {
@@ -1268,6 +1269,7 @@ template <class T> inline void findtransit(int i, int j, T dt0, State<T>& s, Der
     if (iter >= ITMAX || dt0 == tt1 || dt0 == tt2) break;
   }
   if (newton_iters) *newton_iters += iter;
+  if (iter >= ITMAX) itmax_hits() += 1;   // instrumentation only (tests compare how often the 20-iteration cap fires)
   if (grad) {
     set_state(s, tt.s_prior);
     d.zero_out();

@@ -76,7 +76,7 @@ int nbgo_integrate(int n, double* x, double* v, const double* m, const uint8_t* 
 
 // (intr)(s,tt;grad) Transits.jl:140-180.  ntbv = 1 (TransitTiming) or 3 (TransitParameters).
 // Output layouts are Julia's: tt[i + n*k] (ttbv[c + 3*(i + n*k)]), dtdq0[i + n*(k + ntt*(q + 7*p))] (with c fastest when ntbv=3).
-// stats[0..2] (nullable) += findtransit Newton iterations, kepler-solver calls, gamma Newton iterations.
+// stats[0..3] (nullable) += findtransit Newton iterations, kepler-solver calls, gamma Newton iterations, transits that hit ITMAX.
 int nbgo_transit_timing(int n, double* x, double* v, const double* m, const uint8_t* pair, const double* jac_init, double* t, double h, double tmax,
                         int ti, int ntt, int ntbv, int grad, double* tt, long* count, double* dtdq0, double* dtdelements, double* xerr,
                         double* verr, double* jac_step, double* jac_err, double* dqdt, long* stats_out) {
@@ -85,6 +85,7 @@ int nbgo_transit_timing(int n, double* x, double* v, const double* m, const uint
   TransitOut<double> to(n, ntt, ti, ntbv);
   long newton = 0;
   Stats before = stats();
+  const long itmax_before = itmax_hits();
   integrate_transits(s, to, h, tmax, grad != 0, &newton);
   store_state(s, x, v, xerr, verr, jac_step, jac_err, dqdt, t);
   std::memcpy(tt, to.tt.data(), sizeof(double) * to.tt.size());
@@ -95,6 +96,7 @@ int nbgo_transit_timing(int n, double* x, double* v, const double* m, const uint
     stats_out[0] += newton;
     stats_out[1] += stats().kepler_calls - before.kepler_calls;
     stats_out[2] += stats().newton_iters - before.newton_iters;
+    stats_out[3] += itmax_hits() - itmax_before;   // transits whose findtransit! Newton loop ran into its 20-iteration cap
   }
   return 0;
 }
@@ -104,7 +106,7 @@ int nbgo_transit_timing(int n, double* x, double* v, const double* m, const uint
 // except x, v (for checks).  Returns total findtransit Newton iterations in *newton_total.
 int nbgo_batch_transit_timing(long nsys, int n, double* x, double* v, const double* m, const double* jac_init, double t0, double h, double tmax,
                               int ti, int ntt, int grad, double* tt, long* count, double* dtdq0, double* dtdelements, int nthreads,
-                              long* newton_total) {
+                              long* newton_total, long* itmax_per_system /* nullable: transits of each system that hit ITMAX */) {
   std::atomic<long> next(0), newton(0);
   const int M = 7 * n;
   auto work = [&]() {
@@ -112,12 +114,13 @@ int nbgo_batch_transit_timing(long nsys, int n, double* x, double* v, const doub
       long b = next.fetch_add(1);
       if (b >= nsys) break;
       double t = t0;
-      long st[3] = {0, 0, 0};
+      long st[4] = {0, 0, 0, 0};
       nbgo_transit_timing(n, x + (size_t)b * 3 * n, v + (size_t)b * 3 * n, m + (size_t)b * n, nullptr, jac_init ? jac_init + (size_t)b * M * M : nullptr,
                           &t, h, tmax, ti, ntt, 1, grad, tt + (size_t)b * n * ntt, count + (size_t)b * n,
                           dtdq0 ? dtdq0 + (size_t)b * n * ntt * M : nullptr, dtdelements ? dtdelements + (size_t)b * n * ntt * M : nullptr, nullptr,
                           nullptr, nullptr, nullptr, nullptr, st);
       newton += st[0];
+      if (itmax_per_system) itmax_per_system[b] = st[3];
     }
   };
   std::vector<std::thread> th;

@@ -231,3 +231,35 @@ def test_cfg3_full_length_oracle_vs_recorded_gpu_state(oracle):
     xg, vg = np.array(g["x"]), np.array(g["v"])
     assert np.max(np.abs(xg - s["x"])) / np.max(np.abs(s["x"])) < 5e-11
     assert np.max(np.abs(vg - s["v"])) / np.max(np.abs(s["v"])) < 5e-10
+
+
+def test_cfg2_full_length_oracle_vs_quad_golden(oracle, elements):
+    # BASELINE cfg 2 at its full length (TRAPPIST-1, 1600 d = 26,667 steps of 0.06 d, grad = true): the Float64 oracle against the SAME
+    # algorithm evaluated in __float128 from the same Float64 inputs (tests/golden/cfg2_quad_system0.npz, generated by
+    # tools/gen_quad_golden.py through the oracle's nbgoq_transit_timing_grad).  This pins (i) that the two are one algorithm -- same
+    # transit counts, all 2,768 transit times within 1e-11 -- and (ii) the Float64 round-off floor of the reference algorithm at this
+    # length, which the GPU test (test_cfg2_full_length_1600_days) uses as its yardstick.  Also the short-run consistency of the quad
+    # driver with the Float64 one (9 d: everything within 1e-13).
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg2_quad_system0.npz"))
+    t0, h, tmax, ntt = float(g["t0"]), float(g["h"]), float(g["tmax"]), int(g["ntt"])
+    assert (t0, h, tmax, ntt) == (7257.0, 0.06, 1600.0, 1062)
+    x, v, jac = oracle.init_nbody(elements, t0)
+    rel = lambda a, b: np.max(np.abs(np.asarray(a) - b)) / np.max(np.abs(b))
+    nq = oracle.ntt(9.0, elements[1:, 1])
+    s9 = oracle.new_state(x, v, elements[:, 0], t0)
+    r9 = oracle.transit_timing(s9, h, 9.0, nq, grad=True, jac_init=jac)
+    q9 = oracle.quad_transit_timing_grad(x, v, elements[:, 0], jac, t0, h, 9.0, nq)
+    assert np.array_equal(r9["count"], q9["count"]) and rel(r9["tt"], q9["tt"]) < 1e-15
+    assert rel(r9["dtdq0"], q9["dtdq0"]) < 1e-13 and rel(r9["dtdelements"], q9["dtdelements"]) < 1e-13 and rel(s9["jac_step_cm"], q9["jac_step_cm"]) < 1e-13
+    s = oracle.new_state(x, v, elements[:, 0], t0)
+    r = oracle.transit_timing(s, h, tmax, ntt, grad=True, jac_init=jac)
+    assert np.array_equal(r["count"], g["count"]) and r["count"].sum() == 2768
+    mask = g["tt"] != 0
+    assert np.array_equal(mask, r["tt"] != 0)
+    assert np.max(np.abs(r["tt"][mask] - g["tt"][mask]) / np.abs(g["tt"][mask])) < 1e-11
+    pick = lambda a: np.stack([a[i, k] for i, k in g["rows"]])
+    floor = {"x": rel(s["x"], g["x"]), "v": rel(s["v"], g["v"]), "jac_step": rel(s["jac_step_cm"], g["jac_step_cm"]),
+             "dtdq0": rel(pick(r["dtdq0"]), g["dtdq0_rows"]), "dtdelements": rel(pick(r["dtdelements"]), g["dtdelements_rows"])}
+    print("Float64 round-off floor of the reference algorithm at 26,667 steps (relative max-norm vs __float128):", floor)
+    assert floor["x"] < 1e-10 and floor["v"] < 1e-10 and floor["jac_step"] < 1e-8 and floor["dtdq0"] < 1e-8 and floor["dtdelements"] < 1e-8
