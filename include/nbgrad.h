@@ -171,7 +171,7 @@ int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, c
  * For a multi-device plan the counters are summed over the slices and the timings are the maximum over the slices.
  * nbg_last_timings: device milliseconds (CUDA events on the plan's stream) spent in the last compute call in the
  *  trajectory kernel [0], transit-refinement kernel [1], Jacobian kernel [2], everything else [3]; [4] = total;
- *  [5] = dense phisalpha-operator kernel; [6] = pair-operator kernel (split path); [7] reserved (0). */
+ *  [5] = dense phisalpha-operator kernel; [6] = pair-operator kernel (split path); [7] = transit adjoint kernel. */
 int32_t nbg_counters(nbg_plan* plan, int64_t* c8);
 int32_t nbg_counters_reset(nbg_plan* plan);
 int32_t nbg_last_timings(nbg_plan* plan, double* ms8);

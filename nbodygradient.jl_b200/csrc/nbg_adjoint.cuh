@@ -21,7 +21,7 @@
 // relative to the terms (parity tests at 1e-11 unchanged).  The Kahan error terms take part as jac_step + jac_error, which is what the
 // first compensated addition of the reference's step sees (utils.jl:36-46).
 #pragma once
-#include "nbg_jacobian.cuh"
+#include "nbg_jacobian_rx.cuh"
 
 namespace nbg {
 
@@ -137,14 +137,14 @@ __device__ __forceinline__ void adjoint_step(AdjVec<NMAX> (&Z)[NC], const Src& S
     int rec = 2 * P - 1;
     for (int i = 0; i <= n - 2; ++i)
       for (int j = i + 1; j <= n - 1; ++j, --rec)
-        if (!kicks || !((kmask >> rx_pair_index_rt(n, i, j)) & 1u)) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
+        if (!kicks || !((kmask >> rx_pair_index(n, i, j)) & 1u)) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
   }
   adj_dense<NC>(Z, S, phi_dense_offset(n, kicks, kicks ? 1 : 0), n, 0.0, false);   // phic! + phisalpha!
   {  // ascending sweep reversed
     int rec = P - 1;
     for (int i = n - 2; i >= 0; --i)
       for (int j = n - 1; j >= i + 1; --j, --rec)
-        if (!kicks || !((kmask >> rx_pair_index_rt(n, i, j)) & 1u)) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
+        if (!kicks || !((kmask >> rx_pair_index(n, i, j)) & 1u)) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
   }
   if (kicks) adj_dense<NC>(Z, S, phi_dense_offset(n, true, 0), n, h2, true);       // first kickfast! + drift (quirk B-3)
   else drift_t();

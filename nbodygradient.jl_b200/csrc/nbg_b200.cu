@@ -32,6 +32,7 @@
 
 #include "../../include/nbgrad.h"
 #include "nbg_jacobian_rx.cuh"
+#include "nbg_adjoint.cuh"
 #ifdef NBG_EXPERIMENTS
 #include "nbg_jacobian_mma.cuh"   // DMMA Jacobian kernel: measured 12-18 % slower, kept as evidence
 #endif
@@ -66,7 +67,8 @@ struct EventQueue {
   double *dt0, *t;   // initial guess / time of the prior state
   double* snap;      // [12N][cap]  x, v, xe, ve
   double* hdr;       // [HDR][cap]  dx, dy, dvx, dvy, 1/gdot, 1/vsky, dvdt, dt0_final, chi^2 weight, chi^2 term  (written by transit_kernel)
-  double* stream;    // [step_fields][nq] operator stream of the final step (sized from the actual count)
+  double* stream;    // [step_fields][nq] operator stream of the final step (sized from the actual count): read by transit_adjoint_kernel
+  double* z;         // [nq][C][7N] adjoint vectors of the transit sub-step (nbg_adjoint.cuh): d out_c / d q0 = z_c^T jac_step
 };
 constexpr int HDR = 10;
 
@@ -283,11 +285,57 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Jacobian kernel: one block per system, blockDim = 32*ceil(M/32) threads, thread c owns column c.
-__global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, int n, size_t ld, const double* stream,
-                           int nsteps, double h, const int32_t* evlist, EventQueue Q, int ti, TransitOut O, int stage_phi) {
+// z = T^T w of every queued transit of the chunk (nbg_adjoint.cuh): one thread per transit, NC = 1 (TransitTiming) or 3
+// (TransitParameters: time, v_sky, b_sky^2).  Reads the operator block of the transit's final step (written by transit_kernel and
+// phi_dense_kernel) and the header (sky-plane separations, 1/gdot, ...); writes z scaled so that the Jacobian kernel's dot product
+// IS the output:  out_c[col] = z_c^T J[:, col] (+ zm of the body whose mass column it is).
+template <int NC>
+__global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int nq, int n, int ti, uint32_t kmask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nq) return;
+  const size_t cap = Q.cap;
+  const int occ = Q.body[e];
+  const double dx = Q.hdr[0 * cap + e], dy = Q.hdr[1 * cap + e], dvx = Q.hdr[2 * cap + e], dvy = Q.hdr[3 * cap + e];
+  const double gdinv = Q.hdr[4 * cap + e], vskyinv = Q.hdr[5 * cap + e], dvdt = Q.hdr[6 * cap + e], dt0 = Q.hdr[7 * cap + e];
+  AdjVec<NMAX> Z[NC];
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+    for (int r = 0; r < 3 * n; ++r) { Z[q].zx[r] = 0.0; Z[q].zv[r] = 0.0; }
+    for (int r = 0; r < n; ++r) Z[q].zm[r] = 0.0;
+  }
+  // dtbvdq! (timing.jl:155-194): rows x0, x1, v0, v1 of the occultor minus those of the transited body
+  //   time:    -(dJx0 dvx + dJx1 dvy + dJv0 dx + dJv1 dy) / gdot
+  //   v_sky:   (dJv0 dvx + dJv1 dvy) / vsky + dvdt * d time        b_sky^2:  2 (dJx0 dx + dJx1 dy)
+  Z[0].zx[3 * occ] = dvx; Z[0].zx[3 * occ + 1] = dvy; Z[0].zv[3 * occ] = dx; Z[0].zv[3 * occ + 1] = dy;
+  Z[0].zx[3 * ti] = -dvx; Z[0].zx[3 * ti + 1] = -dvy; Z[0].zv[3 * ti] = -dx; Z[0].zv[3 * ti + 1] = -dy;
+  if (NC == 3) {
+    Z[NC - 2].zv[3 * occ] = dvx * vskyinv; Z[NC - 2].zv[3 * occ + 1] = dvy * vskyinv;
+    Z[NC - 2].zv[3 * ti] = -dvx * vskyinv; Z[NC - 2].zv[3 * ti + 1] = -dvy * vskyinv;
+    Z[NC - 1].zx[3 * occ] = 2.0 * dx; Z[NC - 1].zx[3 * occ + 1] = 2.0 * dy;
+    Z[NC - 1].zx[3 * ti] = -2.0 * dx; Z[NC - 1].zx[3 * ti + 1] = -2.0 * dy;
+  }
+  const Src S{Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
+  adjoint_step<NC>(Z, S, n, 0.5 * dt0, kmask);
+  double* out = Q.z + (size_t)e * NC * 7 * n;
+  for (int r = 0; r < 3 * n; ++r) { out[r] = -gdinv * Z[0].zx[r]; out[3 * n + r] = -gdinv * Z[0].zv[r]; }
+  for (int r = 0; r < n; ++r) out[6 * n + r] = -gdinv * Z[0].zm[r];
+  if (NC == 3) {
+    double* o1 = out + 7 * n;
+    double* o2 = out + 14 * n;
+    for (int r = 0; r < 3 * n; ++r) {
+      o1[r] = fma(dvdt, out[r], Z[NC - 2].zx[r]); o1[3 * n + r] = fma(dvdt, out[3 * n + r], Z[NC - 2].zv[r]);
+      o2[r] = Z[NC - 1].zx[r]; o2[3 * n + r] = Z[NC - 1].zv[r];
+    }
+    for (int r = 0; r < n; ++r) { o1[6 * n + r] = fma(dvdt, out[6 * n + r], Z[NC - 2].zm[r]); o2[6 * n + r] = Z[NC - 1].zm[r]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Jacobian kernel (generic N; used for N = 15, 16): one block per system, blockDim = 32*ceil(M/32) threads, thread c owns column c.
+__global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, int n, size_t ld, const double* stream,
+                           int nsteps, double h, const int32_t* evlist, EventQueue Q, TransitOut O, int stage_phi) {
   extern __shared__ double sm[];
-  const int M = 7 * n, R6 = 6 * n, P = npairs(n);
+  const int M = 7 * n, R6 = 6 * n;
   const long sys = blockIdx.x;
   const int tid = threadIdx.x, nthr = blockDim.x, c = tid;
   JacSmem S;
@@ -296,7 +344,6 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   S.da = S.Je + (size_t)R6 * M;
   S.rec = S.da + (size_t)3 * n * M;
   S.phi = stage_phi ? S.rec + 2 * KF : nullptr;
-  (void)P;
   const size_t jsz = (size_t)R6 * M;
   for (size_t q = tid; q < jsz; q += nthr) { S.Jv[q] = Jv_g[sys * jsz + q]; S.Je[q] = Je_g[sys * jsz + q]; }
   __syncthreads();
@@ -308,37 +355,23 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
     if (evlist) {
       for (int i = 0; i < n; ++i) {
         const int32_t slot = evlist[((size_t)s * n + i) * ld + sys];
-        if (slot < 0) continue;  // uniform across the block
-        // save the prior matrix (set_state!(s_prior,...)), apply the transit step, emit dtbvdq!, restore
-        __syncthreads();
-        for (size_t q = tid; q < jsz; q += nthr) { Jbak[sys * 2 * jsz + q] = S.Jv[q]; Jbak[sys * 2 * jsz + jsz + q] = S.Je[q]; }
-        __syncthreads();
+        if (slot < 0 || c >= M) continue;
+        // transit of body i found after this step: its outputs are z^T jac_step with the adjoint vectors of the sub-step (nbg_adjoint.cuh)
         const size_t cap = Q.cap;
-        const double dt0 = Q.hdr[7 * cap + slot];
-        Src ev{Q.stream + tile_offset(sf, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE)};
-        jac_apply_step(S, ev, n, M, c, 0.5 * dt0, tid, nthr);
-        if (c < M) {
-          const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
-          const double gdinv = Q.hdr[4 * cap + slot];
-          const int j = i;  // occultor
-          const double jx0 = S.Jv[(6 * j) * M + c] - S.Jv[(6 * ti) * M + c], jx1 = S.Jv[(6 * j + 1) * M + c] - S.Jv[(6 * ti + 1) * M + c];
-          const double jv0 = S.Jv[(6 * j + 3) * M + c] - S.Jv[(6 * ti + 3) * M + c], jv1 = S.Jv[(6 * j + 4) * M + c] - S.Jv[(6 * ti + 4) * M + c];
-          const double dtdq = -(jx0 * dvx + jx1 * dvy + jv0 * dx + jv1 * dy) * gdinv;
-          const size_t rec = out_rec(O, sys, j, Q.k[slot], slot);
-          if (O.gq) { gacc = fma(Q.hdr[8 * cap + slot], dtdq, gacc); if (c == 0) cacc += Q.hdr[9 * cap + slot]; }
-          if (!O.dtdq0) {
-          } else if (O.C == 1) {
-            O.dtdq0[rec * M + c] = dtdq;
-          } else {
-            const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
-            O.dtdq0[(rec * M + c) * 3] = dtdq;
-            O.dtdq0[(rec * M + c) * 3 + 1] = (jv0 * dvx + jv1 * dvy) * vskyinv + dvdt * dtdq;
-            O.dtdq0[(rec * M + c) * 3 + 2] = 2.0 * (jx0 * dx + jx1 * dy);
-          }
+        const size_t rec = out_rec(O, sys, i, Q.k[slot], slot);
+        for (int comp = 0; comp < O.C; ++comp) {
+          const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
+          double a = 0.0;
+          for (int b = 0; b < n; ++b)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              a = fma(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c], a);
+              a = fma(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c], a);
+            }
+          if (c % 7 == 6) a += __ldg(z + 6 * n + c / 7);
+          if (comp == 0 && O.gq) { gacc = fma(Q.hdr[8 * cap + slot], a, gacc); if (c == 0) cacc += Q.hdr[9 * cap + slot]; }
+          if (O.dtdq0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
         }
-        __syncthreads();
-        for (size_t q = tid; q < jsz; q += nthr) { S.Jv[q] = Jbak[sys * 2 * jsz + q]; S.Je[q] = Jbak[sys * 2 * jsz + jsz + q]; }
-        __syncthreads();
       }
     }
   }
@@ -356,30 +389,53 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 // warps per SM (255 registers, 136-219 KB of operator ring)
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
-// SPB systems per block (1 or 2).  With 2, the two systems' warps that share an SM sub-partition run the same straight-line
-// instruction stream side by side (one barrier pattern per work item for both), so they share instruction fetches: the fully
-// unrolled step is 85 KB of code, executed once per step and warp, and instruction fetch is the kernel's top stall (ncu r01h).
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, int SPB = 1>
-__global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
-    jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
-                  int nsteps_in, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
-                  uint32_t kmask, long nsys, long sys0) {
+// Outputs of one queued transit from the register-resident matrix: out_comp[c] = z_comp^T J[:, c] with the adjoint vectors of the transit
+// sub-step (nbg_adjoint.cuh).  The x half sums the x rows, the v half the v rows; one shuffle joins them.  Offset 0 (position = body).
+template <int N>
+__device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int half, int c,
+                                               bool valid, int tid, double* __restrict__ acc) {
+  constexpr int M = 7 * N;
+  const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
+  for (int comp = 0; comp < O.C; ++comp) {
+    const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
+    const double* __restrict__ zh = z + 3 * N * half;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int b = 0; b < N; ++b) {
+      a0 = fma(__ldg(zh + 3 * b), S.jv[b][0], a0);
+      a1 = fma(__ldg(zh + 3 * b + 1), S.jv[b][1], a1);
+      a2 = fma(__ldg(zh + 3 * b + 2), S.jv[b][2], a2);
+    }
+    double a = (a0 + a1) + a2;
+    a += shx(a);
+    if (valid && c % 7 == 6) a += __ldg(z + 6 * N + c / 7);   // mass rows of jac_step are unit rows
+    if (comp == 0 && O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
+      // (accumulators in shared memory: transits are rare, and two more live doubles would spill in the step loop)
+      acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], a, acc[tid]);
+      if (tid == 0) acc[blockDim.x] += Q.hdr[9 * (size_t)Q.cap + slot];
+    }
+    if (O.dtdq0 && valid && half == 0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
+  }
+}
+
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
+__global__ void __launch_bounds__(rx_warps(N) * 32, MB)
+    jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, size_t ld, const double* __restrict__ stream, int nsteps, double h,
+                  const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, TransitOut O, uint32_t kmask, long nsys) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int NS = KICK ? 3 : 1;  // dense operators per step (nbg_kicks.cuh)
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + NS * PF) + NS * 12 * N * N /* stream */,
                 SB = 2 * P * KF + NS * 12 * N * N /* staged */, G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + NS * PF) / 4, G1 = NS * 3 * N * N,
                 NT = rx_warps(N) * 32;
-  static_assert(SPB == 1 || !KICK, "the fast-kick variant runs one system per block");
-  const int slot_in_block = SPB == 1 ? 0 : (int)threadIdx.x / NT;
-  const int tid = SPB == 1 ? (int)threadIdx.x : (int)threadIdx.x % NT;
-  double* const smsys = smrx + (size_t)slot_in_block * 2 * SB;
+  const int tid = (int)threadIdx.x;
   double* const hold = smrx + 2 * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
-  const long sys_raw = sys0 + (long)blockIdx.x * SPB + slot_in_block;   // the launch covers systems sys0 .. nsys-1 (a slice of the batch)
-  const bool live = sys_raw < nsys;            // odd batch: the last block's second slot only takes part in the barriers
-  const long sys = live ? sys_raw : nsys - 1;
-  const int nsteps = live ? nsteps_in : 0;
+  double* const acc = smrx + 2 * SB + (KICK ? 3 * N * NT : 0);  // fused chi^2: NT gradient accumulators + the chi^2 sum of this chunk
+  const long sys = blockIdx.x;
+  if (sys >= nsys) return;
+  acc[tid] = 0.0;
+  if (tid == 0) acc[NT] = 0.0;
   const int lane = tid & 31, warp = tid >> 5, half = lane >> 4, c = warp * 16 + (lane & 15);
-  const bool valid = c < M && live;
+  const bool valid = c < M;
   RxState<N> S;
 #pragma unroll
   for (int b = 0; b < N; ++b)
@@ -389,94 +445,23 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
       S.jv[b][k] = valid ? Jv_g[q] : 0.0;
       S.je[b][k] = valid ? Je_g[q] : 0.0;
     }
-  double* const buf0 = smsys;
-  double* const buf1 = smsys + SB;
+  double* const buf0 = smrx;
+  double* const buf1 = smrx + SB;
   const size_t ntiles = ld / TILE;
-  if (live) rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
-  // One loop over work items -- a main step, or the extra step of a queued transit -- so that rx_step<N> (13k
-  // instructions, fully unrolled) exists once in the instruction stream.
-  double* const bk = Jbak + (size_t)sys * 6 * N * NT + tid;
-  const size_t cap = Q.cap;
-  int s = 0, ev_i = 0;
-  int32_t slot = -1;
-  uint32_t pend = 0;  // bodies with a queued transit at the end of step s (read at the start of the step, used at its end)
-  bool in_event = false;
-  double gacc = 0.0, cacc = 0.0;  // fused chi^2 accumulators of this chunk (column c of the gradient; thread 0: the chi^2 terms)
-  while (true) {
+  if (nsteps > 0) rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+  for (int s = 0; s < nsteps; ++s) {
     double* const cur = (s & 1) ? buf1 : buf0;
-    double h2;
-    const bool fin = !in_event && s >= nsteps;
-    if (SPB == 1) {
-      if (fin) break;
-    } else {  // every work item has the same barrier pattern (two), whatever its kind, so the systems of a block stay side by side
-      if (__syncthreads_and(fin)) break;
-      if (fin) { __syncthreads(); __syncthreads(); continue; }
-    }
-    if (!in_event) {
-      pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
-      __pipeline_wait_prior(0);
-      __syncthreads();  // step s operators visible; everyone is done with the other buffer
-      if (s + 1 < nsteps)
-        rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
-      if (SPB > 1) __syncthreads();
-      h2 = 0.5 * h;
-    } else {
-      __syncthreads();  // everyone is done with cur
-      rx_fetch(cur, Q.stream + tile_offset(SFS, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE), G0, GSKIP, G1, tid, NT);
-      // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
-#pragma unroll
-      for (int b = 0; b < N; ++b)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { bk[(size_t)(3 * b + k) * NT] = S.jv[b][k]; bk[(size_t)(3 * N + 3 * b + k) * NT] = S.je[b][k]; }
-      __pipeline_wait_prior(0);
-      __syncthreads();
-      h2 = 0.5 * Q.hdr[7 * cap + slot];
-    }
-    rx_step<N, U, SYNC, KICK>(S, cur, h2, half, c, kmask, hold, NT);
-    if (in_event) {
-      // dtbvdq! (timing.jl:155-194): rows x0,x1 (x half) and v0,v1 (v half) of occultor ev_i and transited body ti
-      double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-      for (int b = 0; b < N; ++b) {
-        const double sg = (b == ev_i ? 1.0 : 0.0) - (b == ti ? 1.0 : 0.0);
-        d0 = fma(sg, S.jv[b][0], d0);
-        d1 = fma(sg, S.jv[b][1], d1);
-      }
-      const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
-      const double gdinv = Q.hdr[4 * cap + slot];
-      const double mine = (half == 0) ? (d0 * dvx + d1 * dvy) : (d0 * dx + d1 * dy);
-      const double other = shx(mine);
-      const double dtdq = -(mine + other) * gdinv;  // meaningful in the x half
-      const size_t rec = out_rec(O, sys, ev_i, Q.k[slot], slot);
-      if (O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
-        gacc = fma(Q.hdr[8 * cap + slot], dtdq, gacc);
-        if (tid == 0) cacc += Q.hdr[9 * cap + slot];
-      }
-      if (!O.dtdq0) {
-      } else if (O.C == 1) {
-        if (valid && half == 0) O.dtdq0[rec * M + c] = dtdq;
-      } else {
-        const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
-        const double s2 = shx(d0 * dvx + d1 * dvy);  // x half receives (jv0 dvx + jv1 dvy)
-        if (valid && half == 0) {
-          O.dtdq0[(rec * M + c) * 3] = dtdq;
-          O.dtdq0[(rec * M + c) * 3 + 1] = s2 * vskyinv + dvdt * dtdq;
-          O.dtdq0[(rec * M + c) * 3 + 2] = 2.0 * (d0 * dx + d1 * dy);
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < N; ++b)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { S.jv[b][k] = bk[(size_t)(3 * b + k) * NT]; S.je[b][k] = bk[(size_t)(3 * N + 3 * b + k) * NT]; }
-    }
-    // next work item: remaining queued transits of step s, else step s + 1
-    in_event = pend != 0u;
-    if (in_event) {
-      ev_i = __ffs(pend) - 1;
+    uint32_t pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;   // bodies with a queued transit at the end of step s
+    __pipeline_wait_prior(0);
+    __syncthreads();  // step s operators visible; everyone is done with the other buffer
+    if (s + 1 < nsteps)
+      rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+    rx_step<N, U, SYNC, KICK>(S, cur, 0.5 * h, half, c, kmask, hold, NT);
+    while (pend != 0u) {  // uniform across the block
+      const int body = __ffs(pend) - 1;
       pend &= pend - 1u;
-      slot = evlist[((size_t)s * N + ev_i) * ld + sys];
-    } else {
-      ++s;
+      const int32_t slot = evlist[((size_t)s * N + body) * ld + sys];
+      rx_transit_out<N>(S, Q, O, sys, body, slot, half, c, valid, tid, acc);
     }
   }
   if (valid) {
@@ -489,25 +474,24 @@ __global__ void __launch_bounds__(rx_warps(N) * 32 * SPB, MB)
         Je_g[q] = S.je[b][k];
       }
   }
-  if (O.gq && evlist && live) {
-    if (valid && half == 0) O.gq[(size_t)sys * M + c] += gacc;
-    if (tid == 0) O.chi2[sys] += cacc;
+  if (O.gq && evlist) {
+    if (valid && half == 0) O.gq[(size_t)sys * M + c] += acc[tid];
+    if (tid == 0) O.chi2[sys] += acc[NT];
   }
 }
 
 #ifdef NBG_EXPERIMENTS
 // DMMA Jacobian kernel (nbg_jacobian_mma.cuh): one block per system, mma_warps(N) warps, two 8-column tiles per warp; the same
-// work-item loop, operator staging and transit handling as jac_rx_kernel.  No fast-kick pairs (those run jac_rx_kernel<KICK>).
+// operator staging and transit handling as jac_rx_kernel.  No fast-kick pairs (those run jac_rx_kernel<KICK>).
 template <int N, int MB, int TPW>
 __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
-    jac_mma_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, double* __restrict__ Jbak, size_t ld, const double* __restrict__ stream,
-                   int nsteps, double h, const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O,
-                   long nsys, long sys0) {
+    jac_mma_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, size_t ld, const double* __restrict__ stream, int nsteps, double h,
+                   const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, TransitOut O, long nsys) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + PF) + 12 * N * N /* stream */, SB = 2 * P * KF + 12 * N * N /* staged */,
                 G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = mma_warps(N, TPW) * 32;
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long sys = sys0 + (long)blockIdx.x;
+  const long sys = blockIdx.x;
   if (sys >= nsys) return;
   const MmaLane L = mma_lane(lane, warp, N, TPW);
   const bool val[2] = {L.c[0] < M && L.t < 3, TPW > 1 && L.c[1] < M && L.t < 3};
@@ -525,91 +509,39 @@ __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
   double* const buf0 = smrx;
   double* const buf1 = smrx + SB;
   const size_t ntiles = ld / TILE;
-  rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
-  double* const bk = Jbak + (size_t)sys * 4 * TPW * N * NT + tid;
-  const size_t cap = Q.cap;
-  int s = 0, ev_i = 0;
-  int32_t slot = -1;
-  uint32_t pend = 0;
-  bool in_event = false;
-  while (in_event || s < nsteps) {
+  if (nsteps > 0) rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+  for (int s = 0; s < nsteps; ++s) {
     double* const cur = (s & 1) ? buf1 : buf0;
-    double h2;
-    if (!in_event) {
-      pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
-      __pipeline_wait_prior(0);
-      __syncthreads();  // step s operators visible; everyone is done with the other buffer
-      if (s + 1 < nsteps)
-        rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
-      h2 = 0.5 * h;
-    } else {
-      __syncthreads();  // everyone is done with cur
-      rx_fetch(cur, Q.stream + tile_offset(SFS, 0, 0, (size_t)slot), TILE, (size_t)(slot % TILE), G0, GSKIP, G1, tid, NT);
-      // save the prior matrix (set_state!(s_prior, s)) while the transit operators arrive
+    uint32_t pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;
+    __pipeline_wait_prior(0);
+    __syncthreads();  // step s operators visible; everyone is done with the other buffer
+    if (s + 1 < nsteps)
+      rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+    mma_step<N, TPW>(S, cur, 0.5 * h, L);
+    while (pend != 0u) {
+      const int body = __ffs(pend) - 1;
+      pend &= pend - 1u;
+      const int32_t slot = evlist[((size_t)s * N + body) * ld + sys];
+      // out_comp[c] = z_comp^T J[:, c] (nbg_adjoint.cuh): lane t of a column group holds rows x_t and v_t of every body
+      const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
+      for (int comp = 0; comp < O.C; ++comp) {
+        const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
 #pragma unroll
-      for (int T = 0; T < TPW; ++T)
+        for (int T = 0; T < TPW; ++T) {
+          double a = 0.0;
+          if (L.t < 3) {
 #pragma unroll
-        for (int b = 0; b < N; ++b)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            bk[(size_t)((T * N + b) * 2 + e) * NT] = S.jv[T][b][e];
-            bk[(size_t)(2 * TPW * N + (T * N + b) * 2 + e) * NT] = S.je[T][b][e];
+            for (int b = 0; b < N; ++b) {
+              a = fma(__ldg(z + 3 * b + L.t), S.jv[T][b][0], a);
+              a = fma(__ldg(z + 3 * N + 3 * b + L.t), S.jv[T][b][1], a);
+            }
           }
-      __pipeline_wait_prior(0);
-      __syncthreads();
-      h2 = 0.5 * Q.hdr[7 * cap + slot];
-    }
-    mma_step<N, TPW>(S, cur, h2, L);
-    if (in_event) {
-      // dtbvdq! (timing.jl:155-194): lane t = 0 holds rows x0, v0 and lane t = 1 rows x1, v1 of occultor ev_i minus transited body ti
-      const double dx = Q.hdr[0 * cap + slot], dy = Q.hdr[1 * cap + slot], dvx = Q.hdr[2 * cap + slot], dvy = Q.hdr[3 * cap + slot];
-      const double gdinv = Q.hdr[4 * cap + slot];
-      const size_t rec = out_rec(O, sys, ev_i, Q.k[slot], slot);
-#pragma unroll
-      for (int T = 0; T < TPW; ++T) {
-        double jx = 0.0, jw = 0.0;
-#pragma unroll
-        for (int b = 0; b < N; ++b) {
-          const double sg = (b == ev_i ? 1.0 : 0.0) - (b == ti ? 1.0 : 0.0);
-          jx = fma(sg, S.jv[T][b][0], jx);
-          jw = fma(sg, S.jv[T][b][1], jw);
-        }
-        const double px = L.t == 0 ? jx * dvx : (L.t == 1 ? jx * dvy : 0.0);   // (jx0 dvx, jx1 dvy)
-        const double pv = L.t == 0 ? jw * dx : (L.t == 1 ? jw * dy : 0.0);     // (jv0 dx,  jv1 dy)
-        const double a = px + __shfl_xor_sync(FULL, px, 1), bq = pv + __shfl_xor_sync(FULL, pv, 1);
-        const double dtdq = -(a + bq) * gdinv;
-        if (O.C == 1) {
-          if (val[T] && L.t == 0) O.dtdq0[rec * M + L.c[T]] = dtdq;
-        } else {
-          const double vskyinv = Q.hdr[5 * cap + slot], dvdt = Q.hdr[6 * cap + slot];
-          const double qv = L.t == 0 ? jw * dvx : (L.t == 1 ? jw * dvy : 0.0);  // (jv0 dvx, jv1 dvy)
-          const double qx = L.t == 0 ? jx * dx : (L.t == 1 ? jx * dy : 0.0);    // (jx0 dx,  jx1 dy)
-          const double s2 = qv + __shfl_xor_sync(FULL, qv, 1), s3 = qx + __shfl_xor_sync(FULL, qx, 1);
-          if (val[T] && L.t == 0) {
-            O.dtdq0[(rec * M + L.c[T]) * 3] = dtdq;
-            O.dtdq0[(rec * M + L.c[T]) * 3 + 1] = s2 * vskyinv + dvdt * dtdq;
-            O.dtdq0[(rec * M + L.c[T]) * 3 + 2] = 2.0 * s3;
-          }
+          a += __shfl_xor_sync(FULL, a, 1);
+          a += __shfl_xor_sync(FULL, a, 2);
+          if (val[T] && L.c[T] % 7 == 6) a += __ldg(z + 6 * N + L.c[T] / 7);
+          if (O.dtdq0 && val[T] && L.t == 0) O.dtdq0[(rec * M + L.c[T]) * O.C + comp] = a;
         }
       }
-#pragma unroll
-      for (int T = 0; T < TPW; ++T)
-#pragma unroll
-        for (int b = 0; b < N; ++b)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            S.jv[T][b][e] = bk[(size_t)((T * N + b) * 2 + e) * NT];
-            S.je[T][b][e] = bk[(size_t)(2 * TPW * N + (T * N + b) * 2 + e) * NT];
-          }
-    }
-    // next work item: remaining queued transits of step s, else step s + 1
-    in_event = pend != 0u;
-    if (in_event) {
-      ev_i = __ffs(pend) - 1;
-      pend &= pend - 1u;
-      slot = evlist[((size_t)s * N + ev_i) * ld + sys];
-    } else {
-      ++s;
     }
   }
 #pragma unroll
@@ -627,13 +559,13 @@ __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
 }
 
 template <int N, int MB, int TPW>
-int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
-                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, long sys0) {
+int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h,
+                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, const TransitOut& O) {
   constexpr int P = N * (N - 1) / 2, SB = 2 * P * KF + 12 * N * N;
   const size_t smem = (size_t)2 * SB * 8;
   if (cudaFuncSetAttribute(jac_mma_kernel<N, MB, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   cudaFuncSetAttribute(jac_mma_kernel<N, MB, TPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_mma_kernel<N, MB, TPW><<<(unsigned)(nsys - sys0), mma_warps(N, TPW) * 32, smem, st>>>(Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, nsys, sys0);
+  jac_mma_kernel<N, MB, TPW><<<(unsigned)nsys, mma_warps(N, TPW) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, nsys);
   return 0;
 }
 #endif  // NBG_EXPERIMENTS
@@ -741,34 +673,35 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
     case 12: phi_dense_kernel<12><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 13: phi_dense_kernel<13><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
     case 14: phi_dense_kernel<14><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;
+    case 15: phi_dense_kernel<15><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;   // N = 15, 16: only the queued transits
+    case 16: phi_dense_kernel<16><<<grid, block, 0, st>>>(base, ntiles, nitems, nitems_dev, kf); break;   // (their adjoint needs the dense operator)
     default: return -1;
   }
   return 0;
 }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, int SPB = 1>
-int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
-                  const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u, long sys0 = 0) {
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
+int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h, const int32_t* evlist,
+                  const uint32_t* evmask, const EventQueue& Q, const TransitOut& O, uint32_t kmask = 0u) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
-  const size_t smem = ((size_t)2 * SB * SPB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0)) * 8;
+  const size_t smem = ((size_t)2 * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0) + rx_warps(N) * 32 + 1) * 8;
   // per launch, not once: function attributes are per device, and plans of one process may live on different devices
-  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, SPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, SPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_rx_kernel<N, U, SYNC, MB, KICK, SPB><<<(unsigned)((nsys - sys0 + SPB - 1) / SPB), rx_warps(N) * 32 * SPB, smem, st>>>(
-      Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask, nsys, sys0);
+  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask, nsys);
   return 0;
 }
 // fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
-int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* Je, double* Jbak, size_t ld, const double* stream, int nsteps, double h,
-                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask) {
+int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h,
+                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, const TransitOut& O, uint32_t kmask) {
   switch (n) {
-    case 2: return launch_jac_rx<2, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
-    case 3: return launch_jac_rx<3, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
-    case 4: return launch_jac_rx<4, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
-    case 5: return launch_jac_rx<5, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
-    case 6: return launch_jac_rx<6, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
-    case 7: return launch_jac_rx<7, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
-    case 8: return launch_jac_rx<8, 1, true, 1, true>(st, nsys, Jv, Je, Jbak, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 2: return launch_jac_rx<2, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 3: return launch_jac_rx<3, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 4: return launch_jac_rx<4, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 5: return launch_jac_rx<5, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 6: return launch_jac_rx<6, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 7: return launch_jac_rx<7, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 8: return launch_jac_rx<8, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
   }
   return -1;
 }
@@ -978,8 +911,8 @@ struct nbg_plan {
   TrajArrays T{};
   DevBuf bx, bv, bxe, bve, bm, bdq, bgs, bt, bterr, bcount, bstatus;
   DevBuf bbackup;  // trajectory state at the start of a chunk: a chunk whose transit queue overflowed is re-run from it
-  DevBuf bJv, bJe, bJbak, bstream, bscal, bevlist, bevmask;
-  DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream;
+  DevBuf bJv, bJe, bstream, bscal, bevlist, bevmask;
+  DevBuf qn, qsys, qstep, qbody, qk, qdt0, qt, qsnap, qhdr, qstream, qz;
   DevBuf btt, bdtdq0, bdtde, bjinit, bntt, boff, bcounters, belem;
   DevBuf bevtt, bevd, beve;            // event-row outputs of one chunk (one-shot calls)
   DevBuf bchi2, bgq, btobs, bsigma;    // fused likelihood
@@ -1158,7 +1091,6 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   const size_t M = 7 * (size_t)n, C = p->C;
   const bool kicks = p->kmask != 0u;
   const size_t sf = step_fields(n, kicks);
-  const size_t jsz = (size_t)6 * n * 7 * n;
   const bool rows = detect && p->sink.active;            // per-chunk event rows, streamed to the host
   const bool fused = detect && grad && p->fused;        // chi^2 gradient accumulated in the Jacobian kernel
   // chunk length from the stream budget
@@ -1190,7 +1122,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     bad |= p->qhdr.ensure((size_t)HDR * cap * 8);
     if (bad) return fail(NBG_ERR_NOMEM, "transit queue allocation failed");
     Q = EventQueue{p->qn.as<int32_t>(), (int32_t)cap, p->qsys.as<int32_t>(), p->qstep.as<int32_t>(), p->qbody.as<int32_t>(), p->qk.as<int32_t>(),
-                   p->qdt0.as<double>(), p->qt.as<double>(), p->qsnap.as<double>(), p->qhdr.as<double>(), p->qstream.as<double>()};
+                   p->qdt0.as<double>(), p->qt.as<double>(), p->qsnap.as<double>(), p->qhdr.as<double>(), p->qstream.as<double>(), p->qz.as<double>()};
     return 0;
   };
   // trajectory state saved at the start of every chunk with detection: x, v, xe, ve, gsave, t, terr, count
@@ -1222,13 +1154,6 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     if (bad) return fail(NBG_ERR_NOMEM, "event list allocation failed");
     evlist = p->bevlist.as<int32_t>();
     evmask = p->bevmask.as<uint32_t>();
-  }
-  if (grad && detect) {
-    size_t per_sys = std::max<size_t>(2 * jsz, (size_t)6 * n * rx_warps(n) * 32);
-#ifdef NBG_EXPERIMENTS
-    per_sys = std::max<size_t>(per_sys, (size_t)8 * n * std::max(mma_warps(n, 2) * 2, mma_warps(n, 1)) * 16);
-#endif
-    if (p->bJbak.ensure((size_t)nsys * per_sys * 8)) return fail(NBG_ERR_NOMEM, "Jacobian backup allocation failed");
   }
   const bool use_rx = n <= NBG_RX_MAX_BODIES && (!p->force_generic_jac || kicks);
   if (kicks && n > 8) return fail(NBG_ERR_UNSUPPORTED, "fast-kick pairs (s.pair) are supported for nbody <= 8");
@@ -1337,8 +1262,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     if (detect) {
       // per-transit buffers from the measured count
       const size_t nqp = (size_t)round32(std::max<long>(nq, 1));
-      if (grad && p->qstream.ensure_grow(sf * nqp * 8)) return fail(NBG_ERR_NOMEM, "transit operator stream allocation failed");
+      if (grad && (p->qstream.ensure_grow(sf * nqp * 8) || p->qz.ensure_grow(nqp * C * M * 8)))
+        return fail(NBG_ERR_NOMEM, "transit operator stream allocation failed");
       Q.stream = p->qstream.as<double>();
+      Q.z = p->qz.as<double>();
       O = TransitOut{p->btt.as<double>(), grad ? p->bdtdq0.as<double>() : nullptr, p->bntt.as<int32_t>(), p->boff.as<int32_t>(), p->RT, p->C, 0,
                      nullptr, nullptr, 0, nullptr, nullptr};
       if (rows) {
@@ -1379,11 +1306,18 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         else transit_kernel<false><<<gridT, tpb, 0, p->stream>>>(p->T, n, Q, ti, O, dcount, p->kmask, p->newton_pre);
         tm.end();
         p->launches++;
-        if (grad && use_rx) {
+        if (grad) {
+          // dense phisalpha operator of every transit's final step, then the adjoint vectors z = T^T w of the sub-step (nbg_adjoint.cuh):
+          // the Jacobian kernel turns them into dt/dq0 (or the chi^2 gradient) with one dot product per column
           tm.begin(5);
           if (launch_phi_dense(p->stream, n, Q.stream, 0, nq, nullptr, 1, kicks, p->phi_cached)) return fail(NBG_ERR_CUDA, "phi_dense launch failed");
           tm.end();
-          p->launches++;
+          tm.begin(7);
+          const unsigned gridZ = (unsigned)((nq + 63) / 64);
+          if (C == 3) transit_adjoint_kernel<3><<<gridZ, 64, 0, p->stream>>>(Q, (int)nq, n, ti, p->kmask);
+          else transit_adjoint_kernel<1><<<gridZ, 64, 0, p->stream>>>(Q, (int)nq, n, ti, p->kmask);
+          tm.end();
+          p->launches += 2;
         }
       }
     }
@@ -1396,44 +1330,43 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       if (use_rx) {
         const int32_t* evl = detect ? evlist : nullptr;
         const uint32_t* evm = detect ? evmask : nullptr;
-        double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>(), *Jb = p->bJbak.as<double>();
+        double *Jv = p->bJv.as<double>(), *Je = p->bJe.as<double>();
         const double* strm = p->bstream.as<double>();
+        cudaStream_t st = p->stream;
         int rc = 0;
-        const long hi = nsys, lo = 0;
-        if (kicks) rc = launch_jac_rx_kicked(n, p->stream, nsys, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, p->kmask);
+        if (kicks) rc = launch_jac_rx_kicked(n, st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O, p->kmask);
         else switch (n) {
-          case 2: rc = launch_jac_rx<2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 3: rc = launch_jac_rx<3, 3>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 4: rc = launch_jac_rx<4, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 5: rc = launch_jac_rx<5, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 6: rc = launch_jac_rx<6, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 7: rc = launch_jac_rx<7, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 9: rc = launch_jac_rx<9, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 2: rc = launch_jac_rx<2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 3: rc = launch_jac_rx<3, 3>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 4: rc = launch_jac_rx<4, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 5: rc = launch_jac_rx<5, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 6: rc = launch_jac_rx<6, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 7: rc = launch_jac_rx<7, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 9: rc = launch_jac_rx<9, 1, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
           case 10:  // two blocks of 5 warps per SM at 168 registers (spills ~45 doubles): measured 1.25x faster than one block at 255
-            rc = launch_jac_rx<10, 1, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+            rc = launch_jac_rx<10, 1, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O);
             break;
-          case 11: rc = launch_jac_rx<11, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 12: rc = launch_jac_rx<12, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 13: rc = launch_jac_rx<13, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
-          case 14: rc = launch_jac_rx<14, 1, true, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break;
+          case 11: rc = launch_jac_rx<11, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 12: rc = launch_jac_rx<12, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 13: rc = launch_jac_rx<13, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 14: rc = launch_jac_rx<14, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
           default:
 #ifdef NBG_EXPERIMENTS
-            // measured and rejected: the DMMA kernel, pivot blocks of 2 with a barrier per group (22), two systems per block
-            // in lockstep (48), pivot blocks of 2 at 3 blocks/SM (other values)
-            if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
-            if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, lo); break; }
-            if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break; }
-            if (p->rx_unroll == 48) { rc = launch_jac_rx<8, 8, false, 1, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break; }
-            if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo); break; }
+            // measured and rejected: the DMMA kernel, pivot blocks of 2 with a barrier per group (22), pivot blocks of 2 at
+            // 3 blocks/SM (other values)
+            if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
+            if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
+            if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
+            if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
 #endif
             // full unroll, no per-group barrier, 2 blocks/SM at 255 registers
-            rc = launch_jac_rx<8, 8, false, 2>(p->stream, hi, Jv, Je, Jb, ld, strm, s, h, evl, evm, Q, ti, O, 0u, lo);
+            rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O);
             break;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
       } else {
-        jac_kernel<<<(unsigned)nsys, tps, smem, p->stream>>>(p->bJv.as<double>(), p->bJe.as<double>(), p->bJbak.as<double>(), n, ld,
-                                                            p->bstream.as<double>(), s, h, detect ? evlist : nullptr, Q, ti, O, stage_phi ? 1 : 0);
+        jac_kernel<<<(unsigned)nsys, tps, smem, p->stream>>>(p->bJv.as<double>(), p->bJe.as<double>(), n, ld, p->bstream.as<double>(), s, h,
+                                                            detect ? evlist : nullptr, Q, O, stage_phi ? 1 : 0);
       }
       tm.end();
       p->launches++;
@@ -1624,7 +1557,7 @@ int32_t nbg_plan_destroy(nbg_plan* p) {
   if (p->aux_stream) cudaStreamSynchronize(p->aux_stream);
   if (p->aux2_stream) cudaStreamSynchronize(p->aux2_stream);
   DevBuf* all[] = {&p->bx, &p->bv, &p->bxe, &p->bve, &p->bm, &p->bdq, &p->bgs, &p->bt, &p->bterr, &p->bcount, &p->bstatus, &p->bbackup, &p->bJv, &p->bJe,
-                   &p->bJbak, &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap,
+                   &p->qz, &p->bstream, &p->bscal, &p->bevlist, &p->bevmask, &p->qn, &p->qsys, &p->qstep, &p->qbody, &p->qk, &p->qdt0, &p->qt, &p->qsnap,
                    &p->qhdr, &p->qstream, &p->btt, &p->bdtdq0, &p->bdtde, &p->bjinit, &p->bntt, &p->boff, &p->bcounters, &p->belem, &p->bevtt, &p->bevd,
                    &p->beve, &p->bchi2, &p->bgq, &p->btobs, &p->bsigma};
   for (auto* b : all) b->release();
@@ -1851,7 +1784,7 @@ static void finish_timings(nbg_plan* p, Timer& tm) {
   const double tot = p->timings[4];
   // pair_op / phi_dense run on the aux stream concurrently with the transit kernel, so the per-kernel times can add up to more
   // than the total; "other" is what is left of the total, never negative
-  p->timings[3] = std::max(0.0, tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6]);
+  p->timings[3] = std::max(0.0, tot - p->timings[0] - p->timings[1] - p->timings[2] - p->timings[5] - p->timings[6] - p->timings[7]);
   unsigned long long dc[8];
   cudaMemcpy(dc, p->bcounters.p, 64, cudaMemcpyDeviceToHost);
   for (int q = 1; q <= 4; ++q) p->counters_host[q] = dc[q];
