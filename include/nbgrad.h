@@ -58,6 +58,7 @@ typedef struct nbg_plan nbg_plan;
 int32_t nbg_version(void);
 const char* nbg_last_error(void);
 int32_t nbg_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+const char* nbg_source_hash(void); /* hash of the sources the library was compiled from (nbgrad/build.py); "unknown" for a hand build */
 int32_t nbg_build_flags(void);  /* bit 0: built with -DNBG_EXPERIMENTS (the rejected kernel variants of DESIGN.md 5 are selectable) */
 
 /* A plan holds device buffers for `nsys` systems of `nbody` bodies on CUDA device `device`.
@@ -105,6 +106,12 @@ int32_t nbg_integrate_resident(nbg_plan* plan, double h, int64_t nsteps, double 
  * x_samples[k][sys][body][3], k = 0 .. ceil(nsteps/stride)-1.  The reference also keeps jac_step per saved State; here the
  * Jacobian is available at the end (nbg_get_state), or per sample by cutting the integration into calls. */
 int32_t nbg_integrate_sampled(nbg_plan* plan, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples);
+
+/* get_orbital_elements(s, ic) (src/outputs/elements.jl:108-137) of the resident state of every system, on the device:
+ * elements_out[sys][body][11] = (m, P, t0 = 0, ecosw, esinw, I, Omega, a, e, omega, tp), the fields of the reference's Elements (body 0 carries
+ * only its mass).  eps = ic.epsilon (Julia column-major n x n) or NULL = fully nested.  Called between integration calls it gives the
+ * elements at sampled steps without moving x, v off the device. */
+int32_t nbg_orbital_elements(nbg_plan* plan, const double* eps, double* elements_out);
 
 /* One-shot form with HOST buffers: set_state + integrate + get_state. */
 int32_t nbg_integrate(nbg_plan* plan, const double* x0, const double* v0, const double* m, const uint8_t* pair, double t0, double h,

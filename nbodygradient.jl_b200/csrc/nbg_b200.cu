@@ -1423,6 +1423,35 @@ int pair_mask(const uint8_t* pair, int n, uint32_t* mask) {
   return 0;
 }
 
+// hierarchy matrix for the device IC / elements kernels: eps (Julia column-major n x n) or NULL = fully nested, plus the elements row of
+// each Keplerian
+int make_hierarchy(IcsHierarchy* Hp, const double* eps, int ni) {
+  IcsHierarchy& H = *Hp;
+  const size_t n = (size_t)ni;
+  std::memset(&H, 0, sizeof(H));
+  if (eps) {
+    for (size_t q = 0; q < n * n; ++q) H.eps[q] = eps[q];
+  } else {  // fully nested: ElementsIC(t0, N::Int, elements) -> hierarchy([N, ones(N-1)...])  (setup_hierarchy.jl:9-29)
+    for (size_t i = 0; i + 1 < n; ++i) {
+      for (size_t j = 0; j <= i; ++j) H.eps[i + n * j] = -1.0;
+      H.eps[i + n * (i + 1)] = 1.0;
+    }
+    for (size_t j = 0; j < n; ++j) H.eps[(n - 1) + n * j] = -1.0;
+  }
+  {  // elements row of each Keplerian: the i+1+b bookkeeping of kepcalc (init_nbody.jl:66-103), a function of eps alone
+    int i = 1, b = 0;
+    while (i < (int)n) {
+      if (H.eps[(i - 1) + 0] == 0.0) b += 1;
+      const int row = i + b;
+      if (row < 0 || row >= (int)n) return fail(NBG_ERR_ARG, "hierarchy matrix does not map Keplerians to element rows");
+      H.row[i - 1] = row;
+      if (b > 0) b -= 2; else if (b < 0) b = 0;
+      i += 1;
+    }
+  }
+  return 0;
+}
+
 // ---- multi-device plans -----------------------------------------------------------------------------------------------------------
 // f(kid, first system of its slice, systems in its slice) runs on one host thread per child plan (= per device slice); the first
 // failure (code and message) is reported to the caller's thread.
@@ -1449,6 +1478,10 @@ extern "C" {
 
 int32_t nbg_version(void) { return 200; }
 const char* nbg_last_error(void) { return g_err.c_str(); }
+#ifndef NBG_SRC_HASH
+#define NBG_SRC_HASH "unknown"
+#endif
+const char* nbg_source_hash(void) { return NBG_SRC_HASH; }
 int32_t nbg_build_flags(void) {
 #ifdef NBG_EXPERIMENTS
   return 1;
@@ -1654,27 +1687,7 @@ int32_t nbg_set_state_elements(nbg_plan* p, const double* elements, const double
   p->generation++;
   const size_t n = p->n, nsys = p->nsys, M = 7 * n;
   IcsHierarchy H;
-  std::memset(&H, 0, sizeof(H));
-  if (eps) {
-    for (size_t q = 0; q < n * n; ++q) H.eps[q] = eps[q];
-  } else {  // fully nested: ElementsIC(t0, N::Int, elements) -> hierarchy([N, ones(N-1)...])  (setup_hierarchy.jl:9-29)
-    for (size_t i = 0; i + 1 < n; ++i) {
-      for (size_t j = 0; j <= i; ++j) H.eps[i + n * j] = -1.0;
-      H.eps[i + n * (i + 1)] = 1.0;
-    }
-    for (size_t j = 0; j < n; ++j) H.eps[(n - 1) + n * j] = -1.0;
-  }
-  {  // elements row of each Keplerian: the i+1+b bookkeeping of kepcalc (init_nbody.jl:66-103), a function of eps alone
-    int i = 1, b = 0;
-    while (i < (int)n) {
-      if (H.eps[(i - 1) + 0] == 0.0) b += 1;
-      const int row = i + b;
-      if (row < 0 || row >= (int)n) return fail(NBG_ERR_ARG, "hierarchy matrix does not map Keplerians to element rows");
-      H.row[i - 1] = row;
-      if (b > 0) b -= 2; else if (b < 0) b = 0;
-      i += 1;
-    }
-  }
+  if (int r = make_hierarchy(&H, eps, (int)n)) return r;
   CK(cudaStreamSynchronize(p->copy_stream));  // a previous jac_init kernel may still read the elements buffer
   if (p->belem.ensure(7 * n * nsys * 8)) return fail(NBG_ERR_NOMEM, "elements allocation failed");
   CK(cudaMemcpyAsync(p->belem.p, elements, 7 * n * nsys * 8, cudaMemcpyHostToDevice, p->stream));
@@ -1868,6 +1881,26 @@ int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t str
   const cudaError_t err = cudaGetLastError();
   sx.release(); sv.release(); ox.release();
   if (err != cudaSuccess) return fail(NBG_ERR_CUDA, cudaGetErrorString(err));
+  return NBG_OK;
+}
+
+// get_orbital_elements(s, ic) (src/outputs/elements.jl:108-137) for the resident state of every system: the adjacent step after the path
+// for RV / astrometry consumers.  eps: hierarchy matrix (Julia column-major n x n) or NULL = fully nested.
+int32_t nbg_orbital_elements(nbg_plan* p, const double* eps, double* elements_out) {
+  if (!p || !elements_out) return fail(NBG_ERR_ARG, "NULL argument");
+  if (!p->kids.empty()) return for_kids(p, [&](nbg_plan* k, long lo, long) { return nbg_orbital_elements(k, eps, elements_out + (size_t)lo * p->n * 11); });
+  if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
+  CK(cudaSetDevice(p->device));
+  IcsHierarchy H;
+  if (int r = make_hierarchy(&H, eps, p->n)) return r;
+  const size_t nsys = p->nsys, bytes = nsys * p->n * 11 * 8;
+  if (p->stage[6].ensure(bytes)) return fail(NBG_ERR_NOMEM, "staging allocation failed");
+  const int tpb = 64;
+  elements_out_kernel<<<(unsigned)((nsys + tpb - 1) / tpb), tpb, 0, p->stream>>>(p->T.x, p->T.v, p->T.m, H, p->n, (long)nsys, p->ld, p->stage[6].as<double>());
+  p->launches++;
+  CK(cudaMemcpyAsync(elements_out, p->stage[6].p, bytes, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  CK(cudaGetLastError());
   return NBG_OK;
 }
 

@@ -271,4 +271,70 @@ __global__ void __launch_bounds__(64) ics_kernel(const double* __restrict__ elem
   }
 }
 
+// ---- Cartesian state -> orbital elements -------------------------------------------------------------------
+// get_orbital_elements(s, ic)   src/outputs/elements.jl:108-137  (get_relative_positions :25-35, get_relative_masses :38-48,
+//                               hvec :55-59, calc_Omega :61-65, calc_omega :67-82, convert_to_elements :84-106)
+// One thread per system; x, v, m: SoA [q][ld] (the resident state).  out[sys][body][11] = (m, P, t0 = 0, ecosw, esinw, I, Omega, a, e,
+// omega, tp), the fields of the reference's Elements; body 0 carries only its mass.
+__device__ __forceinline__ void ics_convert_to_elements(const double* x, const double* v, double Gmm, double* o) {
+  const double R = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const double V = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  double hx = x[1] * v[2] - x[2] * v[1], hy = -(x[0] * v[2] - x[2] * v[0]);
+  const double hz = x[0] * v[1] - x[1] * v[0];
+  if (hz >= 0.0) hy *= -1.0; else hx *= -1.0;
+  const double h = sqrt(hx * hx + hy * hy + hz * hz);
+  const double xv = x[0] * v[0] + x[1] * v[1] + x[2] * v[2];
+  const double Rdot = sgn(xv) * sqrt(V * V - (h / R) * (h / R));
+  const double a = 1.0 / ((2.0 / R) - (V * V) / Gmm);
+  const double e = sqrt(1.0 - (h * h / (Gmm * a)));
+  const double I = acos(hz / h);
+  double Om = 0.0, wpf = 0.0;
+  if (I != 0.0) {
+    const double si = sin(I);
+    Om = atan2(hx / (h * si), hy / (h * si));
+    const double swpf = x[2] / (R * si);
+    const double cwpf = ((x[0] / R) + sin(Om) * swpf * cos(I)) / cos(Om);
+    wpf = atan2(swpf, cwpf);
+  }
+  const double sinf = a * Rdot * (1.0 - e * e) / (h * e), cosf = (a * (1.0 - e * e) / R - 1.0) / e;
+  const double w = wpf - atan2(sinf, cosf);
+  const double P = 6.283185307179586 * sqrt(a * a * a / Gmm);
+  const double n = 6.283185307179586 / P;
+  const double ecw = e * cos(w), esw = e * sin(w);
+  const double tp = fmod(-sqrt(1.0 - e * e) * ecw / (n * (1.0 - esw)) -
+                             (2.0 / n) * atan2(sqrt(1.0 - e) * (esw + ecw + e), sqrt(1.0 + e) * (esw - ecw - e)), P);
+  o[0] = P; o[1] = 0.0; o[2] = ecw; o[3] = esw; o[4] = I; o[5] = Om; o[6] = a; o[7] = e; o[8] = w; o[9] = tp;
+}
+
+__global__ void __launch_bounds__(64) elements_out_kernel(const double* __restrict__ X, const double* __restrict__ V, const double* __restrict__ Mm,
+                                                          IcsHierarchy H, int n, long nsys, size_t ld, double* __restrict__ out) {
+  const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= nsys) return;
+  double m[ICN];
+  for (int i = 0; i < n; ++i) m[i] = Mm[(size_t)i * ld + sys];
+  double* o = out + (size_t)sys * n * 11;
+  for (int q = 0; q < 11 * n; ++q) o[q] = 0.0;
+  o[0] = m[0];
+  int i = 1, b = 0;
+  while (i < n) {  // the Keplerian bookkeeping of get_orbital_elements (elements.jl:118-135)
+    if (H.eps[(i - 1) + 0] == 0.0) b += 1;
+    const int q = i - 1 + b;
+    if (q >= 0 && q < n - 1) {
+      // row q of amat x (init_nbody.jl:176-188), and G sum |eps| m (elements.jl:38-48)
+      double xr[3] = {0, 0, 0}, vr[3] = {0, 0, 0}, mu = 0.0;
+      for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < n; ++l) s += (H.eps[q + n * j] == H.eps[q + n * l]) ? m[l] : 0.0;
+        const double aqj = (H.eps[q + n * j] * m[j]) / s;
+        for (int k = 0; k < 3; ++k) { xr[k] += aqj * X[(size_t)(3 * j + k) * ld + sys]; vr[k] += aqj * V[(size_t)(3 * j + k) * ld + sys]; }
+        mu += fabs(H.eps[q + n * j]) * m[j];
+      }
+      o[11 * i] = m[i];
+      ics_convert_to_elements(xr, vr, kG * mu, o + 11 * i + 1);
+    }
+    if (b > 0) b -= 2; else if (b < 0) i += 1;
+    i += 1;
+  }
+}
+
 }  // namespace nbg

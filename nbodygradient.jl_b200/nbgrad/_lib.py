@@ -13,7 +13,7 @@ ST_NONFINITE, ST_TRANSIT_ITMAX, ST_EVENT_OVERFLOW, ST_NTT_OVERFLOW = 1, 2, 4, 8
 SYMBOLS = ["nbg_version", "nbg_last_error", "nbg_device_count", "nbg_plan_create", "nbg_plan_destroy", "nbg_set_pair", "nbg_set_state", "nbg_set_state_elements", "nbg_get_jac_init", "nbg_get_state",
            "nbg_integrate_resident", "nbg_integrate_sampled", "nbg_integrate", "nbg_transit_timing_resident", "nbg_transit_fetch", "nbg_transit_chi2", "nbg_transit_timing",
            "nbg_counters", "nbg_counters_reset", "nbg_last_timings", "nbg_cuda_stream", "nbg_fp64_peak", "nbg_build_flags", "nbg_plan_create_multi", "nbg_plan_devices",
-           "nbg_state_generation", "nbg_transit_chi2_fused", "nbg_chunk_retries"]
+           "nbg_state_generation", "nbg_transit_chi2_fused", "nbg_chunk_retries", "nbg_orbital_elements", "nbg_source_hash"]
 
 
 class NbgError(RuntimeError):
@@ -32,6 +32,11 @@ def lib():
         for s in SYMBOLS:
             getattr(L, s)
         L.nbg_last_error.restype = C.c_char_p
+        L.nbg_source_hash.restype = C.c_char_p
+        from .build import source_hash
+        if L.nbg_source_hash().decode() != source_hash() and os.environ.get("NBGRAD_ALLOW_STALE") != "1":
+            raise NbgError("libnbgrad_b200.so was built from other sources (%s, sources are %s): run `python -m nbgrad.build --if-stale` "
+                           "(or set NBGRAD_ALLOW_STALE=1)" % (L.nbg_source_hash().decode(), source_hash()))
         L.nbg_cuda_stream.restype = C.c_int64
         L.nbg_chunk_retries.restype = C.c_int64
         L.nbg_state_generation.restype = C.c_int64

@@ -30,21 +30,37 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
-def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in dependencies())
-
-
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    # the hash of the sources is compiled in (nbg_source_hash): a library that does not match the sources next to it is detected at load
+    cmd = [nvcc] + NVCC_FLAGS + ['-DNBG_SRC_HASH="%s"' % source_hash()] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + SOURCES
     subprocess.run(cmd, cwd=CSRC, check=True)
+    os.replace(LIB + ".tmp", LIB)
     return LIB
 
 
+def built_hash():
+    """Source hash compiled into the library on disk, or None."""
+    import ctypes
+    if not os.path.exists(LIB):
+        return None
+    try:
+        L = ctypes.CDLL(LIB)
+        L.nbg_source_hash.restype = ctypes.c_char_p
+        return L.nbg_source_hash().decode()
+    except (OSError, AttributeError):
+        return None
+
+
+def needs_build():
+    return built_hash() != source_hash()
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if "--if-stale" in sys.argv:
+        print("up to date" if not needs_build() else build(force=True))
+    else:
+        print(build(force=True, verbose="-v" in sys.argv))

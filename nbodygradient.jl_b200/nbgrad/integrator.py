@@ -238,6 +238,19 @@ class TransitParameters(_TransitOutput):
         self.dtbvdelements = np.zeros((B, 3, n, ntt, 7, n))
 
 
+class ElementsOutput:
+    """Orbital elements at sampled steps: get_orbital_elements (src/outputs/elements.jl:108-137) applied to the state before every
+    `stride`-th step, as CartesianOutput does for x, v.  The conversion runs on the device on the resident state (nbg_orbital_elements);
+    x, v never leave it.  o.elements[k, b, i, :] = (m, P, t0 = 0, ecosw, esinw, I, Omega, a, e, omega, tp) of body i; o.t[k]."""
+
+    FIELDS = ("m", "P", "t0", "ecosw", "esinw", "I", "Omega", "a", "e", "omega", "tp")
+
+    def __init__(self, nbody, nstep, stride=1, eps=None):
+        self.nbody, self.nstep, self.stride = int(nbody), int(nstep), int(stride)
+        self.eps = None if eps is None else np.asfortranarray(np.asarray(eps, dtype=np.float64))
+        self.elements = self.t = None
+
+
 class CartesianOutput:
     """CartesianOutput(nbody, nstep) -- Outputs.jl:7-17.  The reference deep-copies the whole State before every step; here x and v
     before every `stride`-th step are collected on the device (nbg_integrate_sampled): o.x[k, b, i, :], o.v[k, b, i, :], o.t[k]."""
@@ -284,6 +297,8 @@ class Integrator:
             return self._transits(s, arg, grad)
         if isinstance(arg, CartesianOutput):
             return self._sampled(s, arg, grad)
+        if isinstance(arg, ElementsOutput):
+            return self._sampled_elements(s, arg, grad)
         if isinstance(arg, (int, np.integer)) and not isinstance(arg, bool):
             return self._nsteps(s, int(arg), grad)
         if arg is None:
@@ -329,6 +344,35 @@ class Integrator:
                                                ptr(o.x), ptr(o.v)))
         s._download(plan, grad)
         self._timings(plan)
+
+    # elements at sampled steps: the (intr)(s, o::CartesianOutput) loop with get_orbital_elements applied to each saved state
+    def _sampled_elements(self, s, o, grad):
+        L = _lib.lib()
+        t0 = float(s.t[0])
+        h = self.h * check_step(t0, self.tmax)
+        ns = (o.nstep + o.stride - 1) // o.stride
+        plan = self._p(s)
+        s._upload(plan, grad)
+        o.elements = np.zeros((ns, s.nsys, s.n, 11))
+        o.t = t0 + h * o.stride * np.arange(ns)
+        done = 0
+        for k in range(ns):
+            check(L.nbg_orbital_elements(plan, ptr(o.eps), ptr(o.elements[k])))            # the state BEFORE step k * stride
+            nstep = min(o.stride, o.nstep - done)
+            check(L.nbg_integrate_resident(plan, C.c_double(h), C.c_int64(nstep), C.c_double(0.0), C.c_int32(1 if grad else 0), C.c_int32(1),
+                                           C.c_double(t0 + h * (done + nstep))))
+            done += nstep
+        s._download(plan, grad)
+        self._timings(plan)
+
+    def orbital_elements(self, s, eps=None):
+        """get_orbital_elements(s, ic) of a State as it is now: [b, i, 11] (uploads the state, converts on the device)."""
+        plan = self._p(s)
+        s._upload(plan, False)
+        out = np.zeros((s.nsys, s.n, 11))
+        e = None if eps is None else np.asfortranarray(np.asarray(eps, dtype=np.float64))
+        check(_lib.lib().nbg_orbital_elements(plan, ptr(e), ptr(out)))
+        return out
 
     # (intr)(s, tt; grad) — Transits.jl:140-180
     def _transits(self, s, tt, grad):

@@ -47,6 +47,16 @@ class Oracle:
         self.lib.nbgo_init_nbody(C.c_int(n), _ptr(el), C.c_double(t0), _ptr(epsf), _ptr(x), _ptr(v), _ptr(jac))
         return x, v, jac.T.copy()  # column-major -> [row, col]
 
+    def orbital_elements(self, x, v, m, eps=None):
+        """get_orbital_elements (src/outputs/elements.jl:108-137): returns (n, 11) rows (m, P, t0=0, ecosw, esinw, I, Omega, a, e, omega, tp)."""
+        n = len(m)
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(n, 3)); v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(n, 3))
+        m = np.ascontiguousarray(m, dtype=np.float64)
+        epsf = None if eps is None else np.asfortranarray(np.asarray(eps, dtype=np.float64))
+        out = np.zeros((n, 11))
+        self.lib.nbgo_orbital_elements(C.c_int(n), _ptr(m), _ptr(epsf), _ptr(x), _ptr(v), _ptr(out))
+        return out
+
     def ntt(self, tmax, periods):
         p = np.ascontiguousarray(periods, dtype=np.float64)
         return int(self.lib.nbgo_ntt(C.c_double(tmax), _ptr(p), C.c_int(len(p))))

@@ -41,6 +41,7 @@ inline double m_cosh(double x) { return std::cosh(x); }
 inline double m_exp(double x) { return std::exp(x); }
 inline double m_abs(double x) { return std::fabs(x); }
 inline double m_atan2(double y, double x) { return std::atan2(y, x); }
+inline double m_acos(double x) { return std::acos(x); }
 inline double m_fmod(double x, double y) { return std::fmod(x, y); }
 inline double m_ceil(double x) { return std::ceil(x); }
 inline quad m_sqrt(quad x) { return sqrtq(x); }
@@ -52,6 +53,7 @@ inline quad m_cosh(quad x) { return coshq(x); }
 inline quad m_exp(quad x) { return expq(x); }
 inline quad m_abs(quad x) { return fabsq(x); }
 inline quad m_atan2(quad y, quad x) { return atan2q(y, x); }
+inline quad m_acos(quad x) { return acosq(x); }
 inline quad m_fmod(quad x, quad y) { return fmodq(x, y); }
 inline quad m_ceil(quad x) { return ceilq(x); }
 

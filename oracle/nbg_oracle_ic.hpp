@@ -306,4 +306,65 @@ template <class T> inline State<T> make_state(const ElementsIC<T>& ic) {
   return s;
 }
 
+
+// ---- src/outputs/elements.jl: Cartesian state -> orbital elements ------------------------------------------------------------
+// get_relative_positions :25-35, get_relative_masses :38-48, hvec :55-59, calc_Omega :61-65, calc_omega :67-82,
+// convert_to_elements :84-106, get_orbital_elements :108-137.
+// out[body][11] = (m, P, t0 = 0, ecosw, esinw, I, Omega, a, e, omega, tp) -- the fields of Elements; body 0 carries only its mass.
+template <class T> inline void convert_to_elements(const T* x, const T* v, T Gmm, T* out10) {
+  const T R = m_sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const T V = m_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  // hvec: cross(r, rdot) with the reference's sign conventions (:21, :55-59)
+  T hx = x[1] * v[2] - x[2] * v[1], hy = -(x[0] * v[2] - x[2] * v[0]), hz = x[0] * v[1] - x[1] * v[0];
+  if (hz >= T(0)) hy *= -1; else hx *= -1;
+  const T h = m_sqrt(hx * hx + hy * hy + hz * hz);
+  const T xv = x[0] * v[0] + x[1] * v[1] + x[2] * v[2];
+  const T Rdot = jl_sign(xv) * m_sqrt(V * V - (h / R) * (h / R));
+  const T a = T(1) / ((T(2) / R) - (V * V) / Gmm);
+  const T e = m_sqrt(T(1) - (h * h / (Gmm * a)));
+  const T I = m_acos(hz / h);
+  T Om = T(0);
+  if (I != T(0)) { const T sO = hx / (h * m_sin(I)), cO = hy / (h * m_sin(I)); Om = m_atan2(sO, cO); }
+  T wpf = T(0);
+  if (I != T(0)) {
+    const T swpf = x[2] / (R * m_sin(I));
+    const T cwpf = ((x[0] / R) + m_sin(Om) * swpf * m_cos(I)) / m_cos(Om);
+    wpf = m_atan2(swpf, cwpf);
+  }
+  const T sinf = a * Rdot * (T(1) - e * e) / (h * e), cosf = (a * (T(1) - e * e) / R - T(1)) / e;
+  const T w = wpf - m_atan2(sinf, cosf);
+  const T P = T(2 * PI) * m_sqrt(a * a * a / Gmm);
+  const T n = T(2 * PI) / P;
+  const T ecw = e * m_cos(w), esw = e * m_sin(w);
+  // Julia's % is the truncated remainder (rem), as fmod
+  const T tp = m_fmod(-m_sqrt(T(1) - e * e) * ecw / (n * (T(1) - esw)) -
+                          (T(2) / n) * m_atan2(m_sqrt(T(1) - e) * (esw + ecw + e), m_sqrt(T(1) + e) * (esw - ecw - e)), P);
+  out10[0] = P; out10[1] = T(0); out10[2] = ecw; out10[3] = esw; out10[4] = I; out10[5] = Om; out10[6] = a; out10[7] = e; out10[8] = w; out10[9] = tp;
+}
+template <class T> inline void get_orbital_elements(const ElementsIC<T>& ic, const T* x, const T* v, T* out /* n x 11, row-major [body][field] */) {
+  const int n = ic.n;
+  for (int q = 0; q < 11 * n; ++q) out[q] = T(0);
+  std::vector<T> X(3 * (size_t)n, T(0)), Vv(3 * (size_t)n, T(0)), mu(n > 1 ? n - 1 : 0, T(0));
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < n; ++j) {
+        X[k + 3 * (size_t)i] += ic.amat[i + (size_t)n * j] * x[k + 3 * j];
+        Vv[k + 3 * (size_t)i] += ic.amat[i + (size_t)n * j] * v[k + 3 * j];
+      }
+  for (int i = 0; i < n - 1; ++i) {
+    for (int j = 0; j < n; ++j) mu[i] += m_abs(ic.eps[i + (size_t)n * j]) * ic.m[j];
+    mu[i] *= T(GNEWT);
+  }
+  out[0] = ic.m[0];
+  int i = 1, b = 0;
+  while (i < n) {
+    if (ic.eps[(i - 1) + 0] == T(0)) b += 1;
+    const int q = i - 1 + b;   // 0-based index of X[i+b]
+    out[11 * i] = ic.m[i];
+    convert_to_elements(&X[3 * (size_t)q], &Vv[3 * (size_t)q], mu[q], out + 11 * i + 1);
+    if (b > 0) b -= 2; else if (b < 0) i += 1;
+    i += 1;
+  }
+}
+
 }  // namespace nbgo

@@ -63,6 +63,15 @@ int nbgo_init_nbody(int n, const double* elements, double t0, const double* eps,
   if (jac_init) std::memcpy(jac_init, jj.data(), sizeof(double) * 49 * n * n);
   return 0;
 }
+// get_orbital_elements(s, ic) (src/outputs/elements.jl:108-137): x, v (3 x n column-major) of a State built from masses m and the
+// hierarchy eps (NULL = fully nested) -> out[body][11] = (m, P, t0 = 0, ecosw, esinw, I, Omega, a, e, omega, tp).
+int nbgo_orbital_elements(int n, const double* m, const double* eps, const double* x, const double* v, double* out) {
+  std::vector<double> el((size_t)n * 7, 0.0);
+  for (int i = 0; i < n; ++i) el[i] = m[i];
+  ElementsIC<double> ic = make_elements_ic<double>(0.0, n, el.data(), eps);
+  get_orbital_elements(ic, x, v, out);
+  return 0;
+}
 int nbgo_ntt(double tmax, const double* periods, int n) { return ntt_from_periods(tmax, periods, n); }
 
 // mode 0: (intr)(s,time) Integrator.jl:159-197 ; mode 1: (intr)(s,N) Integrator.jl:211-234

@@ -893,3 +893,45 @@ def test_cartesian_output_sampling(nb, oracle, elements):
     oracle.integrate(so, h, nsteps=nstep - done, grad=True)
     assert rel(s.x[0], so["x"]) < TOL and rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
     assert abs(s.t[0] - (t0 + h * nstep)) < 1e-9
+
+
+def test_orbital_elements_output(nb, oracle, elements):
+    # get_orbital_elements (src/outputs/elements.jl:108-137) on the device.  (i) known answer: at t0 the conversion
+    # returns the elements the system was built from; (ii) the elements before every 7th step of a 50-step integration against the
+    # oracle's restatement applied to the oracle's own states; (iii) a non-nested hierarchy (two binaries).
+    n, t0, h = 8, 7257.0, 0.06
+    B = 3
+    elb = _perturbed_trappist(elements, B, 9)
+    ic = nb.ElementsIC(t0, n, elb)
+    s = nb.State(ic)
+    e0 = nb.Integrator(h, 1.0).orbital_elements(s)
+    for b in range(B):
+        assert np.allclose(e0[b, :, 0], elb[b, :, 0], rtol=0, atol=0)                                   # masses
+        assert rel(e0[b, 1:, 1], elb[b, 1:, 1]) < 1e-11                                                  # P
+        assert np.max(np.abs(e0[b, 1:, 3:5] - elb[b, 1:, 3:5])) < 1e-11                                  # ecosw, esinw
+        assert np.max(np.abs(e0[b, 1:, 5] - elb[b, 1:, 5])) < 1e-11                                      # I
+    o = nb.ElementsOutput(n, 50, 7)
+    nb.Integrator(h, t0 + 100.0)(s, o)
+    assert o.elements.shape == (8, B, n, 11)
+    for b in range(B):
+        x, v, _ = oracle.init_nbody(elb[b], t0)
+        so = oracle.new_state(x, v, elb[b, :, 0], t0)
+        done = 0
+        for k in range(o.elements.shape[0]):
+            if 7 * k > done:
+                oracle.integrate(so, h, nsteps=7 * k - done, grad=False); done = 7 * k
+            ref = oracle.orbital_elements(so["x"], so["v"], elb[b, :, 0])
+            got = o.elements[k, b]
+            assert rel(got[:, [0, 1, 7, 8]], ref[:, [0, 1, 7, 8]]) < TOL                                 # m, P, a, e
+            assert np.max(np.abs(got[:, 3:7] - ref[:, 3:7])) < 1e-10                                     # ecosw, esinw, I, Omega (absolute)
+            dw = np.abs(np.angle(np.exp(1j * (got[1:, 9] - ref[1:, 9]))))                                # omega modulo 2 pi
+            assert np.max(dw * ref[1:, 8]) < 1e-10                                                       # e * d omega
+            assert np.max(np.abs(got[1:, 10] - ref[1:, 10]) / ref[1:, 1]) < 1e-9                         # tp in units of the period
+    # hierarchy of two binaries orbiting each other: H = [4, 2, 1] (setup_hierarchy.jl), elements rows as kepcalc assigns them
+    eps = np.array([[-1.0, 1, 0, 0], [0, 0, -1, 1], [-1, -1, 1, 1], [-1, -1, -1, -1]])
+    el4 = np.array([[1.0, 0, 0, 0, 0, 0, 0], [1e-3, 10.0, 0.3, 0.05, 0.02, 1.4, 0.1], [0.5, 12.0, 0.7, 0.01, -0.03, 1.5, 0.2], [2e-3, 400.0, 1.1, 0.1, 0.05, 1.45, -0.1]])
+    ic4 = nb.ElementsIC(0.0, eps, el4[None])
+    s4 = nb.State(ic4)
+    e4 = nb.Integrator(0.05, 1.0).orbital_elements(s4, eps=ic4.eps)
+    ref4 = oracle.orbital_elements(s4.x[0], s4.v[0], el4[:, 0], eps=ic4.eps)
+    assert rel(e4[0][:, [0, 1, 7, 8]], ref4[:, [0, 1, 7, 8]]) < TOL and np.max(np.abs(e4[0][:, 3:7] - ref4[:, 3:7])) < 1e-10

@@ -1,5 +1,6 @@
 # round 2, second GPU pass: all parity tests, the new bench line, the full-length runs
 mkdir -p gpurun_out
+PYTHONPATH=nbodygradient.jl_b200 python -m nbgrad.build --if-stale 2>&1 | tail -1
 timeout 2400 python -m pytest tests -m gpu -q --maxfail=12 --durations=12 -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|FAILED|deviation|floor|capped|worst|rc=" gpurun_out/pytest_gpu.log | tail -40
 timeout 400 python bench.py > gpurun_out/r02b_bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
