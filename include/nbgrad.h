@@ -173,7 +173,8 @@ int32_t nbg_transit_timing(nbg_plan* plan, const double* x0, const double* v0, c
  *  c[0] main-loop system-steps, c[1] findtransit Newton iterations in the reference's form (full gradient steps; the gradient-free
  *  pre-iterations are not counted), c[2] extra final steps at the converged time (only taken when the last iteration was not already
  *  at it),
- *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main + transit),
+ *  c[3] transits stored, c[4] kernel launches, c[5] Jacobian system-steps applied (main-loop steps; the transit sub-steps are not applied to
+ *  the matrix since v2: their outputs come from adjoint vectors, csrc/nbg_adjoint.cuh),
  *  c[6] steps per chunk of the last call (operator-stream budget), c[7] Jacobian-kernel launches.
  * For a multi-device plan the counters are summed over the slices and the timings are the maximum over the slices.
  * nbg_last_timings: device milliseconds (CUDA events on the plan's stream) spent in the last compute call in the

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int n
 // ------------------------------------------------------------------------------------------------------------------
 // Jacobian kernel (generic N; used for N = 15, 16): one block per system, blockDim = 32*ceil(M/32) threads, thread c owns column c.
 __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, int n, size_t ld, const double* stream,
-                           int nsteps, double h, const int32_t* evlist, EventQueue Q, TransitOut O, int stage_phi) {
+                           int nsteps, double h, const int32_t* evlist, EventQueue Q, int ti, TransitOut O, int stage_phi) {
   extern __shared__ double sm[];
   const int M = 7 * n, R6 = 6 * n;
   const long sys = blockIdx.x;
@@ -365,8 +365,9 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
           for (int b = 0; b < n; ++b)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              a = fma(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c], a);
-              a = fma(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c], a);
+              // rows of body b minus those of the transited body (see rx_transit_out: the x / v parts of z sum to zero over the bodies)
+              a = fma(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c] - S.Jv[(6 * ti + k) * M + c], a);
+              a = fma(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c] - S.Jv[(6 * ti + 3 + k) * M + c], a);
             }
           if (c % 7 == 6) a += __ldg(z + 6 * n + c / 7);
           if (comp == 0 && O.gq) { gacc = fma(Q.hdr[8 * cap + slot], a, gacc); if (c == 0) cacc += Q.hdr[9 * cap + slot]; }
@@ -390,38 +391,74 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
 // Outputs of one queued transit from the register-resident matrix: out_comp[c] = z_comp^T J[:, c] with the adjoint vectors of the transit
-// sub-step (nbg_adjoint.cuh).  The x half sums the x rows, the v half the v rows; one shuffle joins them.  Offset 0 (position = body).
-template <int N>
-__device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int half, int c,
-                                               bool valid, int tid, double* __restrict__ acc) {
-  constexpr int M = 7 * N;
-  const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
-  for (int comp = 0; comp < O.C; ++comp) {
-    const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
-    const double* __restrict__ zh = z + 3 * N * half;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+// sub-step (nbg_adjoint.cuh).  Two things shape this routine:
+//  * accuracy: sum_b z_b J_b is evaluated as sum_b z_b (J_b - J_ti).  The x / v parts of z sum to zero over the bodies (every operator
+//    of the step is translation invariant: pair operators add +g / -g, the drift acts per body, the columns of the force-gradient
+//    operator sum to zero), and the rows of J share a large common mode in the columns of far bodies and masses (barycentre shifts).
+//    The reference forms J'_occ - J'_ti BEFORE multiplying (timing.jl:163-170); multiplying first loses |J| / |J_occ - J_ti| in
+//    relative accuracy (measured 1.6e-8 instead of 2e-12 in the mass-column blocks of dtdelements).
+//  * registers: the dot product runs as a ROLLED loop over rows with both operands in shared memory (this step's operator buffer is free
+//    by now); unrolled with 24 loads in flight it cost the step loop 7 spilled doubles and 6 % of the kernel.
+// scratch: >= 3 * 7N + R * NT doubles, R rows per pass (all 3N rows in one pass for N >= 4).
+template <int N, int NT, int SB>
+__device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int ti, int half,
+                                               int c, bool valid, int tid, double* __restrict__ scratch, double* __restrict__ acc) {
+  constexpr int M = 7 * N, ZMAX = 3 * M, RFIT = (SB - ZMAX) / NT, R = RFIT < 3 * N ? RFIT : 3 * N, NP = (3 * N + R - 1) / R;
+  static_assert(R >= 1, "operator buffer too small for the transit dot product");
+  double* const zs = scratch;         // [C][7N]
+  double* const ex = scratch + ZMAX;  // [R][NT]: this thread's rows of J minus those of the transited body
+  double jt[3] = {0.0, 0.0, 0.0};   // rows of the transited body (ti is a run-time index: selected arithmetically so that jv stays in registers)
 #pragma unroll
-    for (int b = 0; b < N; ++b) {
-      a0 = fma(__ldg(zh + 3 * b), S.jv[b][0], a0);
-      a1 = fma(__ldg(zh + 3 * b + 1), S.jv[b][1], a1);
-      a2 = fma(__ldg(zh + 3 * b + 2), S.jv[b][2], a2);
+  for (int b = 0; b < N; ++b) {
+    const double on = b == ti ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) jt[k] = fma(on, S.jv[b][k], jt[k]);
+  }
+  __syncthreads();  // everyone is done with this step's operators (and with the previous transit's scratch)
+  for (int q = tid; q < O.C * M; q += NT) zs[q] = __ldg(Q.z + (size_t)slot * O.C * M + q);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const bool three = O.C == 3;
+  static_for<0, NP>([&](auto Pc) {
+    constexpr int pass = decltype(Pc)::value;
+    if (pass > 0) __syncthreads();
+    static_for<pass * R, (pass + 1) * R < 3 * N ? (pass + 1) * R : 3 * N>([&](auto Rc) {
+      constexpr int r = decltype(Rc)::value;
+      ex[(r - pass * R) * NT + tid] = S.jv[r / 3][r % 3] - jt[r % 3];
+    });
+    __syncthreads();
+    constexpr int nr = (pass + 1) * R < 3 * N ? R : 3 * N - pass * R;
+    const double* __restrict__ zr = zs + 3 * N * half + pass * R;
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+      const double d = ex[r * NT + tid];
+      a0 = fma(zr[r], d, a0);
+      if (three) { a1 = fma(zr[M + r], d, a1); a2 = fma(zr[2 * M + r], d, a2); }
     }
-    double a = (a0 + a1) + a2;
-    a += shx(a);
-    if (valid && c % 7 == 6) a += __ldg(z + 6 * N + c / 7);   // mass rows of jac_step are unit rows
-    if (comp == 0 && O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
-      // (accumulators in shared memory: transits are rare, and two more live doubles would spill in the step loop)
-      acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], a, acc[tid]);
-      if (tid == 0) acc[blockDim.x] += Q.hdr[9 * (size_t)Q.cap + slot];
-    }
-    if (O.dtdq0 && valid && half == 0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
+  });
+  const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
+  const bool mass = valid && c % 7 == 6;   // mass rows of jac_step are unit rows: column 7p+6 also receives zm[p]
+  const int zm = 6 * N + c / 7;
+  a0 += shx(a0);
+  if (mass) a0 += zs[zm];
+  if (O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
+    acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], a0, acc[tid]);
+    if (tid == 0) acc[NT] += Q.hdr[9 * (size_t)Q.cap + slot];
+  }
+  if (three) {
+    a1 += shx(a1);
+    a2 += shx(a2);
+    if (mass) { a1 += zs[M + zm]; a2 += zs[2 * M + zm]; }
+  }
+  if (O.dtdq0 && valid && half == 0) {
+    if (!three) O.dtdq0[rec * M + c] = a0;
+    else { double* o = O.dtdq0 + (rec * M + c) * 3; o[0] = a0; o[1] = a1; o[2] = a2; }
   }
 }
 
 template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
 __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, size_t ld, const double* __restrict__ stream, int nsteps, double h,
-                  const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, TransitOut O, uint32_t kmask, long nsys) {
+                  const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O, uint32_t kmask, long nsys) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int NS = KICK ? 3 : 1;  // dense operators per step (nbg_kicks.cuh)
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + NS * PF) + NS * 12 * N * N /* stream */,
@@ -461,7 +498,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       const int body = __ffs(pend) - 1;
       pend &= pend - 1u;
       const int32_t slot = evlist[((size_t)s * N + body) * ld + sys];
-      rx_transit_out<N>(S, Q, O, sys, body, slot, half, c, valid, tid, acc);
+      rx_transit_out<N, NT, SB>(S, Q, O, sys, body, slot, ti, half, c, valid, tid, cur, acc);
     }
   }
   if (valid) {
@@ -486,7 +523,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
 template <int N, int MB, int TPW>
 __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
     jac_mma_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, size_t ld, const double* __restrict__ stream, int nsteps, double h,
-                   const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, TransitOut O, long nsys) {
+                   const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O, long nsys) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + PF) + 12 * N * N /* stream */, SB = 2 * P * KF + 12 * N * N /* staged */,
                 G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + PF) / 4, G1 = 3 * N * N, NT = mma_warps(N, TPW) * 32;
@@ -528,12 +565,14 @@ __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
         const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
 #pragma unroll
         for (int T = 0; T < TPW; ++T) {
-          double a = 0.0;
+          double a = 0.0, jt0 = 0.0, jt1 = 0.0;
+#pragma unroll
+          for (int b = 0; b < N; ++b) { const double on = b == ti ? 1.0 : 0.0; jt0 = fma(on, S.jv[T][b][0], jt0); jt1 = fma(on, S.jv[T][b][1], jt1); }
           if (L.t < 3) {
 #pragma unroll
-            for (int b = 0; b < N; ++b) {
-              a = fma(__ldg(z + 3 * b + L.t), S.jv[T][b][0], a);
-              a = fma(__ldg(z + 3 * N + 3 * b + L.t), S.jv[T][b][1], a);
+            for (int b = 0; b < N; ++b) {   // rows of body b minus those of the transited body (see rx_transit_out)
+              a = fma(__ldg(z + 3 * b + L.t), S.jv[T][b][0] - jt0, a);
+              a = fma(__ldg(z + 3 * N + 3 * b + L.t), S.jv[T][b][1] - jt1, a);
             }
           }
           a += __shfl_xor_sync(FULL, a, 1);
@@ -560,12 +599,12 @@ __global__ void __launch_bounds__(mma_warps(N, TPW) * 32, MB)
 
 template <int N, int MB, int TPW>
 int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h,
-                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, const TransitOut& O) {
+                   const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O) {
   constexpr int P = N * (N - 1) / 2, SB = 2 * P * KF + 12 * N * N;
   const size_t smem = (size_t)2 * SB * 8;
   if (cudaFuncSetAttribute(jac_mma_kernel<N, MB, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   cudaFuncSetAttribute(jac_mma_kernel<N, MB, TPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_mma_kernel<N, MB, TPW><<<(unsigned)nsys, mma_warps(N, TPW) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, nsys);
+  jac_mma_kernel<N, MB, TPW><<<(unsigned)nsys, mma_warps(N, TPW) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, nsys);
   return 0;
 }
 #endif  // NBG_EXPERIMENTS
@@ -682,26 +721,26 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
 
 template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h, const int32_t* evlist,
-                  const uint32_t* evmask, const EventQueue& Q, const TransitOut& O, uint32_t kmask = 0u) {
+                  const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
   const size_t smem = ((size_t)2 * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0) + rx_warps(N) * 32 + 1) * 8;
   // per launch, not once: function attributes are per device, and plans of one process may live on different devices
   if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask, nsys);
+  jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask, nsys);
   return 0;
 }
 // fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
 int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h,
-                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, const TransitOut& O, uint32_t kmask) {
+                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask) {
   switch (n) {
-    case 2: return launch_jac_rx<2, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
-    case 3: return launch_jac_rx<3, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
-    case 4: return launch_jac_rx<4, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
-    case 5: return launch_jac_rx<5, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
-    case 6: return launch_jac_rx<6, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
-    case 7: return launch_jac_rx<7, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
-    case 8: return launch_jac_rx<8, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, O, kmask);
+    case 2: return launch_jac_rx<2, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 3: return launch_jac_rx<3, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 4: return launch_jac_rx<4, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 5: return launch_jac_rx<5, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 6: return launch_jac_rx<6, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 7: return launch_jac_rx<7, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 8: return launch_jac_rx<8, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
   }
   return -1;
 }
@@ -1334,39 +1373,39 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
         const double* strm = p->bstream.as<double>();
         cudaStream_t st = p->stream;
         int rc = 0;
-        if (kicks) rc = launch_jac_rx_kicked(n, st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O, p->kmask);
+        if (kicks) rc = launch_jac_rx_kicked(n, st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O, p->kmask);
         else switch (n) {
-          case 2: rc = launch_jac_rx<2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 3: rc = launch_jac_rx<3, 3>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 4: rc = launch_jac_rx<4, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 5: rc = launch_jac_rx<5, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 6: rc = launch_jac_rx<6, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 7: rc = launch_jac_rx<7, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 9: rc = launch_jac_rx<9, 1, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 2: rc = launch_jac_rx<2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 3: rc = launch_jac_rx<3, 3>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 4: rc = launch_jac_rx<4, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 5: rc = launch_jac_rx<5, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 6: rc = launch_jac_rx<6, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 7: rc = launch_jac_rx<7, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 9: rc = launch_jac_rx<9, 1, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 10:  // two blocks of 5 warps per SM at 168 registers (spills ~45 doubles): measured 1.25x faster than one block at 255
-            rc = launch_jac_rx<10, 1, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O);
+            rc = launch_jac_rx<10, 1, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O);
             break;
-          case 11: rc = launch_jac_rx<11, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 12: rc = launch_jac_rx<12, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 13: rc = launch_jac_rx<13, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
-          case 14: rc = launch_jac_rx<14, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break;
+          case 11: rc = launch_jac_rx<11, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 12: rc = launch_jac_rx<12, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 13: rc = launch_jac_rx<13, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 14: rc = launch_jac_rx<14, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
           default:
 #ifdef NBG_EXPERIMENTS
             // measured and rejected: the DMMA kernel, pivot blocks of 2 with a barrier per group (22), pivot blocks of 2 at
             // 3 blocks/SM (other values)
-            if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
-            if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
-            if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
-            if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O); break; }
+            if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
+            if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
+            if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
+            if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
 #endif
             // full unroll, no per-group barrier, 2 blocks/SM at 255 registers
-            rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, O);
+            rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O);
             break;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
       } else {
         jac_kernel<<<(unsigned)nsys, tps, smem, p->stream>>>(p->bJv.as<double>(), p->bJe.as<double>(), n, ld, p->bstream.as<double>(), s, h,
-                                                            detect ? evlist : nullptr, Q, O, stage_phi ? 1 : 0);
+                                                            detect ? evlist : nullptr, Q, ti, O, stage_phi ? 1 : 0);
       }
       tm.end();
       p->launches++;
@@ -2191,7 +2230,7 @@ int32_t nbg_counters(nbg_plan* p, int64_t* c8) {
   }
   for (int q = 0; q < 8; ++q) c8[q] = (int64_t)p->counters_host[q];
   c8[4] = p->launches;
-  c8[5] = (int64_t)(p->counters_host[5] + p->counters_host[4]);
+  c8[5] = (int64_t)p->counters_host[5];   // the Jacobian kernel applies main-loop steps only: transit outputs come from the adjoint vectors
   return NBG_OK;
 }
 int32_t nbg_counters_reset(nbg_plan* p) {

@@ -6,7 +6,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.environ.get("NBGRAD_B200_LIB") or os.path.join(CSRC, "libnbgrad_b200.so")  # env override: A/B builds on the GPU box
 SOURCES = ["nbg_b200.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+# --split-compile 0: ptxas works on the kernels in parallel (1 m 50 s -> 45 s on 8 cores, same register counts)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0"]
 # NBGRAD_EXPERIMENTS=1 also compiles the measured-and-rejected kernel variants (DMMA Jacobian kernel, pivot-block / lockstep variants of
 # jac_rx_kernel: DESIGN.md 5); they double the build time and are off by default
 if os.environ.get("NBGRAD_EXPERIMENTS") == "1":

@@ -594,11 +594,15 @@ inline void compute_jacobian_gamma(const KepParams<T>& P, const T* x0, const T* 
 #define SVE(k_, i_) s.verror[(k_) + 3 * (i_)]
 #define SA(k_, i_) s.a[(k_) + 3 * (i_)]
 
+inline bool& b2_identity() { static thread_local bool f = false; return f; }
 // ---- ahl21.jl:706-760 kepler_driftij_gamma! (grad) ---------------------------
 template <class T> inline void kepler_driftij_gamma(State<T>& s, Derivs<T>& d, int i, int j, T h, bool drift_first) {
   for (int k = 0; k < 3; ++k) { s.x0[k] = SX(k, i) - SX(k, j); s.v0[k] = SV(k, i) - SV(k, j); }
   T gm = T(GNEWT) * (s.m[i] + s.m[j]);
-  if (gm == T(0)) return;  // quirk B-2: returns before clearing jac_ij
+  if (gm == T(0)) {  // quirk B-2: returns before clearing jac_ij (the caller re-applies the previous pair's operator)
+    if (b2_identity()) { Derivs<T>::z(d.jac_ij); for (auto& q : d.dqdt_ij) q = T(0); }   // experiment switch (tests): apply the identity instead
+    return;
+  }
   Derivs<T>::z(d.jac_ij);
   for (int k = 0; k < 6; ++k) s.delxv[k] = T(0);
   Derivs<T>::z(d.jac_kepler); Derivs<T>::z(d.jac_mass);

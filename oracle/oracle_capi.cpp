@@ -51,6 +51,9 @@ template <class T> void apply_map(int map, State<T>& s, T h, long nsteps, int i,
 extern "C" {
 
 int nbgo_version() { return 1; }
+// test switch: 1 = a pair of two massless bodies applies the identity to jac_step (what libnbgrad_b200 does) instead of the reference's
+// stale operator (quirk B-2, ahl21.jl:712-716); affects the calling thread only
+int nbgo_set_b2_identity(int on) { b2_identity() = on != 0; return 0; }
 double nbgo_gnewt() { return GNEWT; }
 
 // ElementsIC(t0, H, elements) -> State(ic): x, v, jac_init.   elements is n x 7 column-major.
