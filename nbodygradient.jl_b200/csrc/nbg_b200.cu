@@ -361,14 +361,15 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
         const size_t rec = out_rec(O, sys, i, Q.k[slot], slot);
         for (int comp = 0; comp < O.C; ++comp) {
           const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
-          double a = 0.0;
+          Dot2 dot;
           for (int b = 0; b < n; ++b)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              // rows of body b minus those of the transited body (see rx_transit_out: the x / v parts of z sum to zero over the bodies)
-              a = fma(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c] - S.Jv[(6 * ti + k) * M + c], a);
-              a = fma(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c] - S.Jv[(6 * ti + 3 + k) * M + c], a);
+              // rows of body b minus those of the transited body, compensated dot product (see transit_column_part)
+              dot.add(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c] - S.Jv[(6 * ti + k) * M + c]);
+              dot.add(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c] - S.Jv[(6 * ti + 3 + k) * M + c]);
             }
+          double a = dot.value();
           if (c % 7 == 6) a += __ldg(z + 6 * n + c / 7);
           if (comp == 0 && O.gq) { gacc = fma(Q.hdr[8 * cap + slot], a, gacc); if (c == 0) cacc += Q.hdr[9 * cap + slot]; }
           if (O.dtdq0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
@@ -390,68 +391,54 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
 // warps per SM (255 registers, 136-219 KB of operator ring)
 template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 6 ? 3 : (N == 5 ? 3 : 6); }
 
-// Outputs of one queued transit from the register-resident matrix: out_comp[c] = z_comp^T J[:, c] with the adjoint vectors of the transit
-// sub-step (nbg_adjoint.cuh).  Two things shape this routine:
-//  * accuracy: sum_b z_b J_b is evaluated as sum_b z_b (J_b - J_ti).  The x / v parts of z sum to zero over the bodies (every operator
-//    of the step is translation invariant: pair operators add +g / -g, the drift acts per body, the columns of the force-gradient
-//    operator sum to zero), and the rows of J share a large common mode in the columns of far bodies and masses (barycentre shifts).
-//    The reference forms J'_occ - J'_ti BEFORE multiplying (timing.jl:163-170); multiplying first loses |J| / |J_occ - J_ti| in
-//    relative accuracy (measured 1.6e-8 instead of 2e-12 in the mass-column blocks of dtdelements).
-//  * registers: the dot product runs as a ROLLED loop over rows with both operands in shared memory (this step's operator buffer is free
-//    by now); unrolled with 24 loads in flight it cost the step loop 7 spilled doubles and 6 % of the kernel.
-// scratch: >= 3 * 7N + R * NT doubles, R rows per pass (all 3N rows in one pass for N >= 4).
-template <int N, int NT, int SB>
-__device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int ti, int half,
-                                               int c, bool valid, int tid, double* __restrict__ scratch, double* __restrict__ acc) {
-  constexpr int M = 7 * N, ZMAX = 3 * M, RFIT = (SB - ZMAX) / NT, R = RFIT < 3 * N ? RFIT : 3 * N, NP = (3 * N + R - 1) / R;
-  static_assert(R >= 1, "operator buffer too small for the transit dot product");
-  double* const zs = scratch;         // [C][7N]
-  double* const ex = scratch + ZMAX;  // [R][NT]: this thread's rows of J minus those of the transited body
-  double jt[3] = {0.0, 0.0, 0.0};   // rows of the transited body (ti is a run-time index: selected arithmetically so that jv stays in registers)
-#pragma unroll
-  for (int b = 0; b < N; ++b) {
-    const double on = b == ti ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) jt[k] = fma(on, S.jv[b][k], jt[k]);
-  }
-  __syncthreads();  // everyone is done with this step's operators (and with the previous transit's scratch)
-  for (int q = tid; q < O.C * M; q += NT) zs[q] = __ldg(Q.z + (size_t)slot * O.C * M + q);
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  const bool three = O.C == 3;
-  static_for<0, NP>([&](auto Pc) {
-    constexpr int pass = decltype(Pc)::value;
-    if (pass > 0) __syncthreads();
-    static_for<pass * R, (pass + 1) * R < 3 * N ? (pass + 1) * R : 3 * N>([&](auto Rc) {
-      constexpr int r = decltype(Rc)::value;
-      ex[(r - pass * R) * NT + tid] = S.jv[r / 3][r % 3] - jt[r % 3];
-    });
-    __syncthreads();
-    constexpr int nr = (pass + 1) * R < 3 * N ? R : 3 * N - pass * R;
-    const double* __restrict__ zr = zs + 3 * N * half + pass * R;
+// ---- outputs of one queued transit: out_comp[c] = z_comp^T J[:, c] with the adjoint vectors of the transit sub-step (nbg_adjoint.cuh) ----
+// Accuracy, two points:
+//  * sum_b z_b J_b is evaluated as sum_b z_b (J_b - J_ti).  The x / v parts of z sum to zero over the bodies (every operator of the step
+//    is translation invariant: pair operators add +g / -g, the drift acts per body, the columns of the force-gradient operator sum to
+//    zero), and the rows of J share a large common mode in the columns of far bodies and masses (barycentre shifts).  The reference
+//    forms J'_occ - J'_ti BEFORE multiplying (timing.jl:163-170); multiplying first would lose |J| / |J_occ - J_ti| in relative accuracy.
+//  * the dot product is compensated (TwoProduct / TwoSum, "Dot2" of Ogita, Rump & Oishi): the reference accumulates the same terms into
+//    jac_step with Kahan compensation, a plain FMA chain over 6N terms would not match that after 26,667 steps of growth of J.
+// One thread's share: its n3 = 3N rows (x rows or v rows of every body, a copy in local memory) against the matching part of z.
+// NOT inlined on purpose: the step loop of jac_rx_kernel sits at the register limit, and this rarely executed code (one transit per ~10
+// system-steps) must not take part in its register allocation (inlined, it cost the loop 7 % -- A/B in profiles/r02c_ab.jsonl).
+__device__ __noinline__ void transit_column_part(const double* __restrict__ jrows, int n3, const double* __restrict__ z, int M, int C, int ti, double* __restrict__ part) {
+  const double jt0 = jrows[3 * ti], jt1 = jrows[3 * ti + 1], jt2 = jrows[3 * ti + 2];
+  for (int comp = 0; comp < C; ++comp) {
+    Dot2 acc;
+    const double* __restrict__ zc = z + (size_t)comp * M;
 #pragma unroll 1
-    for (int r = 0; r < nr; ++r) {
-      const double d = ex[r * NT + tid];
-      a0 = fma(zr[r], d, a0);
-      if (three) { a1 = fma(zr[M + r], d, a1); a2 = fma(zr[2 * M + r], d, a2); }
+    for (int r = 0; r < n3; r += 3) {
+      acc.add(__ldg(zc + r), jrows[r] - jt0);
+      acc.add(__ldg(zc + r + 1), jrows[r + 1] - jt1);
+      acc.add(__ldg(zc + r + 2), jrows[r + 2] - jt2);
     }
-  });
+    part[comp] = acc.value();
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int ti, int half,
+                                               int c, bool valid, int tid, double* __restrict__ acc) {
+  constexpr int M = 7 * N;
+  double rows[3 * N], part[3];
+#pragma unroll
+  for (int b = 0; b < N; ++b)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rows[3 * b + k] = S.jv[b][k];
+  const double* __restrict__ z = Q.z + (size_t)slot * O.C * M;
+  transit_column_part(rows, 3 * N, z + 3 * N * half, M, O.C, ti, part);
   const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
   const bool mass = valid && c % 7 == 6;   // mass rows of jac_step are unit rows: column 7p+6 also receives zm[p]
-  const int zm = 6 * N + c / 7;
-  a0 += shx(a0);
-  if (mass) a0 += zs[zm];
-  if (O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
-    acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], a0, acc[tid]);
-    if (tid == 0) acc[NT] += Q.hdr[9 * (size_t)Q.cap + slot];
-  }
-  if (three) {
-    a1 += shx(a1);
-    a2 += shx(a2);
-    if (mass) { a1 += zs[M + zm]; a2 += zs[2 * M + zm]; }
-  }
-  if (O.dtdq0 && valid && half == 0) {
-    if (!three) O.dtdq0[rec * M + c] = a0;
-    else { double* o = O.dtdq0 + (rec * M + c) * 3; o[0] = a0; o[1] = a1; o[2] = a2; }
+  for (int comp = 0; comp < O.C; ++comp) {
+    double a = part[comp];
+    a += shx(a);
+    if (mass) a += __ldg(z + (size_t)comp * M + 6 * N + c / 7);
+    if (comp == 0 && O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
+      acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], a, acc[tid]);
+      if (tid == 0) acc[blockDim.x] += Q.hdr[9 * (size_t)Q.cap + slot];
+    }
+    if (O.dtdq0 && valid && half == 0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
   }
 }
 
@@ -498,7 +485,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       const int body = __ffs(pend) - 1;
       pend &= pend - 1u;
       const int32_t slot = evlist[((size_t)s * N + body) * ld + sys];
-      rx_transit_out<N, NT, SB>(S, Q, O, sys, body, slot, ti, half, c, valid, tid, cur, acc);
+      rx_transit_out<N>(S, Q, O, sys, body, slot, ti, half, c, valid, tid, acc);
     }
   }
   if (valid) {
