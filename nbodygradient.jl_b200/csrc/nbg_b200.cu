@@ -397,48 +397,66 @@ template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 
 //    is translation invariant: pair operators add +g / -g, the drift acts per body, the columns of the force-gradient operator sum to
 //    zero), and the rows of J share a large common mode in the columns of far bodies and masses (barycentre shifts).  The reference
 //    forms J'_occ - J'_ti BEFORE multiplying (timing.jl:163-170); multiplying first would lose |J| / |J_occ - J_ti| in relative accuracy.
-//  * the dot product is compensated (TwoProduct / TwoSum, "Dot2" of Ogita, Rump & Oishi): the reference accumulates the same terms into
-//    jac_step with Kahan compensation, a plain FMA chain over 6N terms would not match that after 26,667 steps of growth of J.
-// One thread's share: its n3 = 3N rows (x rows or v rows of every body, a copy in local memory) against the matching part of z.
-// NOT inlined on purpose: the step loop of jac_rx_kernel sits at the register limit, and this rarely executed code (one transit per ~10
-// system-steps) must not take part in its register allocation (inlined, it cost the loop 7 % -- A/B in profiles/r02c_ab.jsonl).
-__device__ __noinline__ void transit_column_part(const double* __restrict__ jrows, int n3, const double* __restrict__ z, int M, int C, int ti, double* __restrict__ part) {
-  const double jt0 = jrows[3 * ti], jt1 = jrows[3 * ti + 1], jt2 = jrows[3 * ti + 2];
-  for (int comp = 0; comp < C; ++comp) {
-    Dot2 acc;
-    const double* __restrict__ zc = z + (size_t)comp * M;
-#pragma unroll 1
-    for (int r = 0; r < n3; r += 3) {
-      acc.add(__ldg(zc + r), jrows[r] - jt0);
-      acc.add(__ldg(zc + r + 1), jrows[r + 1] - jt1);
-      acc.add(__ldg(zc + r + 2), jrows[r + 2] - jt2);
-    }
-    part[comp] = acc.value();
-  }
-}
-
-template <int N>
+//  * the dot product is compensated (TwoProduct / TwoSum, Dot2 in nbg_adjoint.cuh): the reference accumulates the same terms into
+//    jac_step with Kahan compensation; a plain FMA chain over 6N terms does not match that once J has grown over 26,667 steps.
+// Registers: the step loop of jac_rx_kernel sits at the 255-register limit and its speed depends on what else ptxas has to fit around it
+// (A/B on one box, ms per 64-step window at 65,536 systems, profiles/r02d_ab.jsonl: dot product unrolled in registers with 24 loads in
+// flight 240.6; as a non-inlined function on a local-memory copy of the rows 242.3; staged through shared memory with a rolled loop 226.3;
+// the r01 kernel that applied a full step per transit 231.2).  So: both operands in shared memory -- this step's operator buffer is
+// free by now -- and a rolled loop over the rows.  scratch: >= 3 * 7N + R * NT doubles, R rows per pass (all 3N rows in one pass for N >= 4).
+template <int N, int NT, int SB>
 __device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int ti, int half,
-                                               int c, bool valid, int tid, double* __restrict__ acc) {
-  constexpr int M = 7 * N;
-  double rows[3 * N], part[3];
+                                               int c, bool valid, int tid, double* __restrict__ scratch, double* __restrict__ acc) {
+  constexpr int M = 7 * N, ZMAX = 3 * M, RFIT = (SB - ZMAX) / NT, R = RFIT < 3 * N ? RFIT : 3 * N, NP = (3 * N + R - 1) / R;
+  static_assert(R >= 1, "operator buffer too small for the transit dot product");
+  double* const zs = scratch;         // [C][7N]
+  double* const ex = scratch + ZMAX;  // [R][NT]: this thread's rows of J minus those of the transited body
+  double jt[3] = {0.0, 0.0, 0.0};   // rows of the transited body (ti is a run-time index: selected arithmetically so that jv stays in registers;
+#pragma unroll                      //  a chain of ?: on the register array becomes an indexed load and moves the matrix to local memory)
+  for (int b = 0; b < N; ++b) {
+    const double on = b == ti ? 1.0 : 0.0;
 #pragma unroll
-  for (int b = 0; b < N; ++b)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) rows[3 * b + k] = S.jv[b][k];
-  const double* __restrict__ z = Q.z + (size_t)slot * O.C * M;
-  transit_column_part(rows, 3 * N, z + 3 * N * half, M, O.C, ti, part);
+    for (int k = 0; k < 3; ++k) jt[k] = fma(on, S.jv[b][k], jt[k]);
+  }
+  __syncthreads();  // everyone is done with this step's operators (and with the previous transit's scratch)
+  for (int q = tid; q < O.C * M; q += NT) zs[q] = __ldg(Q.z + (size_t)slot * O.C * M + q);
+  Dot2 a0, a1, a2;
+  const bool three = O.C == 3;
+  static_for<0, NP>([&](auto Pc) {
+    constexpr int pass = decltype(Pc)::value;
+    if (pass > 0) __syncthreads();
+    static_for<pass * R, (pass + 1) * R < 3 * N ? (pass + 1) * R : 3 * N>([&](auto Rc) {
+      constexpr int r = decltype(Rc)::value;
+      ex[(r - pass * R) * NT + tid] = S.jv[r / 3][r % 3] - jt[r % 3];
+    });
+    __syncthreads();
+    constexpr int nr = (pass + 1) * R < 3 * N ? R : 3 * N - pass * R;
+    const double* __restrict__ zr = zs + 3 * N * half + pass * R;
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+      const double d = ex[r * NT + tid];
+      a0.add(zr[r], d);
+      if (three) { a1.add(zr[M + r], d); a2.add(zr[2 * M + r], d); }
+    }
+  });
   const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
   const bool mass = valid && c % 7 == 6;   // mass rows of jac_step are unit rows: column 7p+6 also receives zm[p]
-  for (int comp = 0; comp < O.C; ++comp) {
-    double a = part[comp];
-    a += shx(a);
-    if (mass) a += __ldg(z + (size_t)comp * M + 6 * N + c / 7);
-    if (comp == 0 && O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
-      acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], a, acc[tid]);
-      if (tid == 0) acc[blockDim.x] += Q.hdr[9 * (size_t)Q.cap + slot];
-    }
-    if (O.dtdq0 && valid && half == 0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
+  const int zm = 6 * N + c / 7;
+  double r0 = a0.value(), r1 = a1.value(), r2 = a2.value();
+  r0 += shx(r0);
+  if (mass) r0 += zs[zm];
+  if (O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
+    acc[tid] = fma(Q.hdr[8 * (size_t)Q.cap + slot], r0, acc[tid]);
+    if (tid == 0) acc[NT] += Q.hdr[9 * (size_t)Q.cap + slot];
+  }
+  if (three) {
+    r1 += shx(r1);
+    r2 += shx(r2);
+    if (mass) { r1 += zs[M + zm]; r2 += zs[2 * M + zm]; }
+  }
+  if (O.dtdq0 && valid && half == 0) {
+    if (!three) O.dtdq0[rec * M + c] = r0;
+    else { double* o = O.dtdq0 + (rec * M + c) * 3; o[0] = r0; o[1] = r1; o[2] = r2; }
   }
 }
 
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       const int body = __ffs(pend) - 1;
       pend &= pend - 1u;
       const int32_t slot = evlist[((size_t)s * N + body) * ld + sys];
-      rx_transit_out<N>(S, Q, O, sys, body, slot, ti, half, c, valid, tid, acc);
+      rx_transit_out<N, NT, SB>(S, Q, O, sys, body, slot, ti, half, c, valid, tid, cur, acc);
     }
   }
   if (valid) {

@@ -48,15 +48,24 @@ def block_dev(a, b, n):
 
 def assert_blocks(name, gpu, ora, exact, n, tol=TOL):
     """Every block of the GPU result agrees with the Float64 oracle to `tol`, or -- where the reference's own Float64 result is not that
-    good (cancellation-prone blocks) -- deviates from the exact (__float128) result by no more than 1.5 x what the oracle does."""
+    good (cancellation-prone blocks) -- is no worse than the oracle measured against the exact (__float128) result (see below)."""
     eg_o = block_dev(gpu, ora, n)
     if exact is None:
         assert eg_o.max() < tol, "%s: worst block deviation GPU vs oracle %.3e" % (name, eg_o.max())
         return eg_o.max()
     eg, eo = block_dev(gpu, exact, n), block_dev(ora, exact, n)
-    ok = (eg_o < tol) | (eg <= 1.5 * eo + 1e-14)
+    # Blocks that miss 1e-11 against the oracle are cancellation-prone blocks in which the oracle itself is not that close to the exact
+    # result.  Per block the two Float64 paths are two realisations of rounding noise (the larger of ~1,000 such ratios exceeds any small
+    # factor), so: no block may be grossly off (10 x the oracle's own error, which catches a lost-cancellation bug: that was 8,000 x),
+    # and over those blocks, and over all blocks, the GPU's RMS deviation from the exact result stays within 2 x / 1.5 x the oracle's.
+    hard = eg_o >= tol
+    ok = ~hard | (eg <= 10.0 * eo + 1e-14)
     assert ok.all(), "%s: %d of %d blocks fail; worst GPU-vs-oracle %.3e, GPU-vs-exact %.3e where oracle-vs-exact is %.3e" % (
         name, int((~ok).sum()), ok.size, eg_o[~ok].max(), eg[~ok].max(), eo[~ok][np.argmax(eg[~ok])])
+    rms = lambda a: float(np.sqrt(np.mean(np.square(a)))) if a.size else 0.0
+    assert rms(eg[hard]) <= 2.0 * rms(eo[hard]) + 1e-14, "%s: %d cancellation-prone blocks, RMS deviation from exact GPU %.3e vs oracle %.3e" % (
+        name, int(hard.sum()), rms(eg[hard]), rms(eo[hard]))
+    assert rms(eg) <= 1.5 * rms(eo) + 1e-15, "%s: RMS block deviation from exact GPU %.3e vs oracle %.3e" % (name, rms(eg), rms(eo))
     return eg_o.max()
 
 
