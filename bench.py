@@ -203,7 +203,7 @@ def roofline_block(L, local, NB, cnt, ksum, ndev=1):
     # algorithmic HBM bytes per main system-step: scalars, compact phisalpha records, Kepler records, dense phisalpha operator, each
     # written once and read once
     P = NB * (NB - 1) // 2
-    stream_bytes = 2 * (2 * P * 32 + P * 24 + 2 * P * 64 + 12 * NB * NB) * 8.0 * (float(cnt[0]) + float(cnt[2]))
+    stream_bytes = 2 * (2 * P * 12 + P * 24 + 2 * P * 64 + 12 * NB * NB) * 8.0 * (float(cnt[0]) + float(cnt[2]))
     hbm_gbs = stream_bytes / (ksum[4] * 1e-3) / 1e9
     return {"bound": "fp64", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
             "traffic": traffic, "traffic_note": why or "dram read+write bytes per launch: ncu-measured bytes per Jacobian step (profiles/r02_jac_rx_profile.json, same sources) x steps per launch",
@@ -522,7 +522,7 @@ def main():
                    "batch_per_gpu": args.nsys, "window_steps": window,
                    "chunk_steps": int(cnt[6]), "jac_launches": int(cnt[7]),
                    "l2": "inputs larger than L2: operator stream %.1f GB + scalar stream %.1f GB per chunk, jac_step %.1f GB per GPU (L2 = 126 MB)" %
-                         ((28 * 152 + 768) * 8 * args.nsys * int(cnt[6]) / 1e9, 56 * 32 * 8 * args.nsys * int(cnt[6]) / 1e9, args.nsys * 48 * 56 * 16 / 1e9),
+                         ((28 * 152 + 768) * 8 * args.nsys * int(cnt[6]) / 1e9, 56 * 12 * 8 * args.nsys * int(cnt[6]) / 1e9, args.nsys * 48 * 56 * 16 / 1e9),
                    "parallelism": ("one process, one multi-device plan (nbg_plan_create_multi), one host thread per GPU" if single else
                                    "one process per GPU (torchrun), systems sharded across GPUs, no collective"),
                    "timing": "host clock between two device-wide synchronisations around blocking calls" if single else "CUDA events on the plan's stream, max over ranks"},

@@ -19,23 +19,11 @@
 //   K0 with quirk B-3 (x' = x + h2 v, v' = v + W0 x_old):  zx' = zx + W0x^T zv, zv' = zv + h2 zx, zm' = zm + W0m^T zv  (simultaneous)
 // Rounding: the same bilinear form summed in another order; agreement with the reference's forward evaluation is at the 1e-15 level
 // relative to the terms (parity tests at 1e-11 unchanged); the Jacobian kernels evaluate the final dot product in difference form
-// (rows of J minus the rows of the transited body) and compensated -- see transit_column_part in nbg_b200.cu.
+// (rows of J minus the rows of the transited body) -- see rx_transit_out in nbg_b200.cu.
 #pragma once
 #include "nbg_jacobian_rx.cuh"
 
 namespace nbg {
-
-// compensated dot product (TwoProduct / TwoSum: "Dot2" of Ogita, Rump & Oishi 2005) for z^T J in the Jacobian kernels
-struct Dot2 {
-  double s = 0.0, c = 0.0;
-  __device__ __forceinline__ void add(double a, double b) {
-    const double p = a * b, pe = fma(a, b, -p);
-    const double t = __dadd_rn(s, p), bb = __dsub_rn(t, s);
-    c += __dadd_rn(__dsub_rn(s, __dsub_rn(t, bb)), __dsub_rn(p, bb)) + pe;
-    s = t;
-  }
-  __device__ __forceinline__ double value() const { return s + c; }
-};
 
 // z layout per transit: [comp][7N] = [zx (3N) | zv (3N) | zm (N)], comp < C
 __host__ __device__ inline size_t zfields(int n, int C) { return (size_t)C * 7 * n; }

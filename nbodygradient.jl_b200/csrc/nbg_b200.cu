@@ -361,15 +361,14 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
         const size_t rec = out_rec(O, sys, i, Q.k[slot], slot);
         for (int comp = 0; comp < O.C; ++comp) {
           const double* __restrict__ z = Q.z + ((size_t)slot * O.C + comp) * M;
-          Dot2 dot;
+          double a = 0.0;
           for (int b = 0; b < n; ++b)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              // rows of body b minus those of the transited body, compensated dot product (see transit_column_part)
-              dot.add(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c] - S.Jv[(6 * ti + k) * M + c]);
-              dot.add(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c] - S.Jv[(6 * ti + 3 + k) * M + c]);
+              // rows of body b minus those of the transited body (see rx_transit_out: the x / v parts of z sum to zero over the bodies)
+              a = fma(__ldg(z + 3 * b + k), S.Jv[(6 * b + k) * M + c] - S.Jv[(6 * ti + k) * M + c], a);
+              a = fma(__ldg(z + 3 * n + 3 * b + k), S.Jv[(6 * b + 3 + k) * M + c] - S.Jv[(6 * ti + 3 + k) * M + c], a);
             }
-          double a = dot.value();
           if (c % 7 == 6) a += __ldg(z + 6 * n + c / 7);
           if (comp == 0 && O.gq) { gacc = fma(Q.hdr[8 * cap + slot], a, gacc); if (c == 0) cacc += Q.hdr[9 * cap + slot]; }
           if (O.dtdq0) O.dtdq0[(rec * M + c) * O.C + comp] = a;
@@ -397,12 +396,12 @@ template <int N> __host__ __device__ constexpr int rx_minblocks() { return N >= 
 //    is translation invariant: pair operators add +g / -g, the drift acts per body, the columns of the force-gradient operator sum to
 //    zero), and the rows of J share a large common mode in the columns of far bodies and masses (barycentre shifts).  The reference
 //    forms J'_occ - J'_ti BEFORE multiplying (timing.jl:163-170); multiplying first would lose |J| / |J_occ - J_ti| in relative accuracy.
-//  * the dot product is compensated (TwoProduct / TwoSum, Dot2 in nbg_adjoint.cuh): the reference accumulates the same terms into
-//    jac_step with Kahan compensation; a plain FMA chain over 6N terms does not match that once J has grown over 26,667 steps.
+//    (A compensated dot product -- TwoProduct / TwoSum -- was measured as well: the full-length deviation of dtdq0 from the __float128
+//    run went from 6.3e-11 to 5.7e-11, i.e. the summation is not what limits it, and the kernel lost 7 %; not kept.)
 // Registers: the step loop of jac_rx_kernel sits at the 255-register limit and its speed depends on what else ptxas has to fit around it
 // (A/B on one box, ms per 64-step window at 65,536 systems, profiles/r02d_ab.jsonl: dot product unrolled in registers with 24 loads in
-// flight 240.6; as a non-inlined function on a local-memory copy of the rows 242.3; staged through shared memory with a rolled loop 226.3;
-// the r01 kernel that applied a full step per transit 231.2).  So: both operands in shared memory -- this step's operator buffer is
+// flight 240.6; as a non-inlined function on a local-memory copy of the rows 242.3; staged through shared memory with a rolled loop 226.3
+// (222.0 on another box, where the r01 kernel that applied a full step per transit took 226.5 and this loop with a compensated sum 237.0).  So: both operands in shared memory -- this step's operator buffer is
 // free by now -- and a rolled loop over the rows.  scratch: >= 3 * 7N + R * NT doubles, R rows per pass (all 3N rows in one pass for N >= 4).
 template <int N, int NT, int SB>
 __device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQueue& Q, const TransitOut& O, long sys, int body, int slot, int ti, int half,
@@ -420,7 +419,7 @@ __device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQ
   }
   __syncthreads();  // everyone is done with this step's operators (and with the previous transit's scratch)
   for (int q = tid; q < O.C * M; q += NT) zs[q] = __ldg(Q.z + (size_t)slot * O.C * M + q);
-  Dot2 a0, a1, a2;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   const bool three = O.C == 3;
   static_for<0, NP>([&](auto Pc) {
     constexpr int pass = decltype(Pc)::value;
@@ -435,14 +434,14 @@ __device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQ
 #pragma unroll 1
     for (int r = 0; r < nr; ++r) {
       const double d = ex[r * NT + tid];
-      a0.add(zr[r], d);
-      if (three) { a1.add(zr[M + r], d); a2.add(zr[2 * M + r], d); }
+      a0 = fma(zr[r], d, a0);
+      if (three) { a1 = fma(zr[M + r], d, a1); a2 = fma(zr[2 * M + r], d, a2); }
     }
   });
   const size_t rec = out_rec(O, sys, body, Q.k[slot], slot);
   const bool mass = valid && c % 7 == 6;   // mass rows of jac_step are unit rows: column 7p+6 also receives zm[p]
   const int zm = 6 * N + c / 7;
-  double r0 = a0.value(), r1 = a1.value(), r2 = a2.value();
+  double r0 = a0, r1 = a1, r2 = a2;
   r0 += shx(r0);
   if (mass) r0 += zs[zm];
   if (O.gq) {  // fused chi^2: d chi2 / d q0[c] += w_transit * d tt / d q0[c]; the chi^2 terms are summed by thread 0 in event order
@@ -616,9 +615,9 @@ int launch_jac_mma(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld
 
 // Split path, second stage: the Kepler operator records of the main steps.  One thread per (system, step, pair section);
 // the 32 lanes of a warp are the systems of one tile, so the section index (hence drift_first) is uniform in a warp and
-// every load/store is a 1 KB run.  Reads the SCF scalars the trajectory kernel left, runs compute_jacobian_gamma!
+// every load/store is a 1 KB run.  Reads the SCF doubles the trajectory kernel left, rebuilds the 22 scalars (kepler_scalars), runs compute_jacobian_gamma!
 // (ahl21.jl:896-1139) in registers and writes the KF-double record the Jacobian kernel consumes.
-__global__ void __launch_bounds__(128, 2) pair_op_kernel(const double* __restrict__ scal, double* __restrict__ stream, int n, size_t ntiles, long nsys) {
+__global__ void __launch_bounds__(128, 2) pair_op_kernel(const double* __restrict__ scal, double* __restrict__ stream, int n, size_t ntiles, long nsys, double h2) {
   const int P = npairs(n);
   const int sec = blockIdx.z * blockDim.y + threadIdx.y;
   const long sys = (long)blockIdx.x * TILE + threadIdx.x;
@@ -631,10 +630,12 @@ __global__ void __launch_bounds__(128, 2) pair_op_kernel(const double* __restric
     const double2 b = __ldg(reinterpret_cast<const double2*>(src + (size_t)g * TILE * 4) + 1);
     in[4 * g] = a.x; in[4 * g + 1] = a.y; in[4 * g + 2] = b.x; in[4 * g + 3] = b.y;
   }
-  double x0[3], v0[3], bim, bjm;
+  double x0[3], v0[3], gamma, kk, bim, bjm;
+  scal_unpack(in, x0, v0, gamma, kk, bim, bjm);
   KepScal S;
-  scal_unpack(in, x0, v0, S, bim, bjm);
+  S.k = kk;
   double rec[KF];
+  if (kk != 0.0) kepler_scalars(x0, v0, kk, h2, sec < P, gamma, &S);
   if (S.k == 0.0) {
 #pragma unroll
     for (int f = 0; f < KF; ++f) rec[f] = 0.0;
@@ -1286,7 +1287,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
       tm.begin(6, aux);
       const int py = 4;
       const dim3 grid((unsigned)(ld / TILE), (unsigned)s_split, (unsigned)((2 * npairs(n) + py - 1) / py)), block(TILE, py);
-      pair_op_kernel<<<grid, block, 0, aux>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys);
+      pair_op_kernel<<<grid, block, 0, aux>>>(p->bscal.as<double>(), p->bstream.as<double>(), n, ld / TILE, nsys, 0.5 * h);
       tm.end();
       p->launches++;
     }

@@ -192,6 +192,48 @@ __device__ __noinline__ void kepler_solve(const double* __restrict__ x0, const d
   P->eta = eta; P->sqb = sqb; P->zeta = zeta;
 }
 
+// The 22 scalars of one pair solve from its inputs and the CONVERGED gamma: everything kepler_solve computes except the cubic guess and
+// the Newton iteration.  pair_op_kernel recomputes them from 10 doubles (x0, v0, gamma, k, m_i, m_j) instead of reading all 22 from the
+// scalar stream: 12 instead of 32 doubles per pair section cross HBM twice (the kernel is HBM-bound).  The values can differ from the
+// trajectory thread's in the last bit (they only feed the Jacobian records).
+__device__ __forceinline__ void kepler_scalars(const double* __restrict__ x0, const double* __restrict__ v0, double k, double h, bool drift_first,
+                                               double gamma, KepScal* __restrict__ P) {
+  const double rt0 = x0[0] - h * v0[0], rt1 = x0[1] - h * v0[1], rt2 = x0[2] - h * v0[2];
+  const double r0 = drift_first ? sqrt(rt0 * rt0 + rt1 * rt1 + rt2 * rt2) : sqrt(x0[0] * x0[0] + x0[1] * x0[1] + x0[2] * x0[2]);
+  const double r0inv = 1.0 / r0;
+  const double beta = 2.0 * k * r0inv - (v0[0] * v0[0] + v0[1] * v0[1] + v0[2] * v0[2]);
+  const double betainv = 1.0 / beta;
+  const double signb = sgn(beta);
+  const double sqb = sqrt(signb * beta);
+  const double zeta = k - r0 * beta;
+  const double eta = drift_first ? (rt0 * v0[0] + rt1 * v0[1] + rt2 * v0[2]) : (x0[0] * v0[0] + x0[1] * v0[1] + x0[2] * v0[2]);
+  double sx, cx;
+  trig_pair(beta > 0.0, 0.5 * gamma, sx, cx);
+  const double g1 = 2.0 * sx * cx / sqb;
+  const double g2 = 2.0 * signb * (sx * sx) * betainv;
+  const double g0 = 1.0 - beta * g2;
+  const double g3 = G3f(gamma, beta, sqb);
+  double h1 = 0.0, h2 = 0.0;
+  const double r = r0 * g0 + eta * g1 + k * g2;
+  const double rinv = 1.0 / r;
+  const double dfdt = -k * g1 * rinv * r0inv;
+  double fm1, gmh, dgdtm1;
+  if (drift_first) {
+    fm1 = -k * r0inv * g2;
+    gmh = k * r0inv * (h * g2 - r0 * g3);
+    dgdtm1 = k * r0inv * rinv * (h * g1 - r0 * g2);
+  } else {
+    h1 = H1f(gamma, beta);
+    h2 = H2f(gamma, beta, sqb);
+    fm1 = k * rinv * (g2 - k * r0inv * h1);
+    gmh = k * rinv * (r0 * h2 + eta * h1);
+    dgdtm1 = -k * rinv * g2;
+  }
+  P->gamma = gamma; P->g0 = g0; P->g1 = g1; P->g2 = g2; P->g3 = g3; P->h1 = h1; P->h2 = h2; P->dfdt = dfdt; P->fm1 = fm1; P->gmh = gmh;
+  P->dgdtm1 = dgdtm1; P->r0 = r0; P->r = r; P->r0inv = r0inv; P->rinv = rinv; P->k = k; P->h = h; P->beta = beta; P->betainv = betainv;
+  P->eta = eta; P->sqb = sqb; P->zeta = zeta;
+}
+
 // compute_jacobian_gamma! (ahl21.jl:896-1139, debug = false)
 // _inl: inlined into pair_op_kernel (everything in registers); the __noinline__ wrapper below is what the one-thread-per-
 // system kernels call twice per pair (keeps their instruction footprint small).

@@ -23,7 +23,7 @@ namespace nbg {
 constexpr int NMAX = 16;  // max bodies per system
 constexpr int KF = 64;    // doubles per Kepler-pair operator record
 constexpr int PF = 24;    // doubles per phisalpha-pair operator record
-constexpr int SCF = 32;   // doubles per pair section in the scalar stream of the split path: x0, v0, the 22 scalars of KepScal, m_i, m_j
+constexpr int SCF = 12;   // doubles per pair section in the scalar stream of the split path: x0, v0, gamma, k, m_i, m_j (+2 pad); see kepler_scalars
 
 // Kepler record fields.  The 6x6 block jac_kepler is stored as four 3x3 blocks ordered for the Jacobian kernel's
 // x-rows / v-rows thread halves: [Kxx, Kxv | Kvv, Kvx], then the mass-column terms split the same way.
@@ -121,19 +121,14 @@ template <bool GRAD> __device__ __forceinline__ void store_body(Body& b, double*
   }
 }
 
-// Packs / unpacks the inputs of kepler_jacobian for the split path (trajectory kernel -> pair_op_kernel).
+// Packs / unpacks what pair_op_kernel needs to rebuild a pair section's operator record (split path, trajectory kernel -> pair_op_kernel).
 __device__ __forceinline__ void scal_pack(double (&rec)[SCF], const double* x0, const double* v0, const KepScal& P, double mi, double mj) {
   rec[0] = x0[0]; rec[1] = x0[1]; rec[2] = x0[2]; rec[3] = v0[0]; rec[4] = v0[1]; rec[5] = v0[2];
-  rec[6] = P.gamma; rec[7] = P.g0; rec[8] = P.g1; rec[9] = P.g2; rec[10] = P.g3; rec[11] = P.h1; rec[12] = P.h2; rec[13] = P.dfdt;
-  rec[14] = P.fm1; rec[15] = P.gmh; rec[16] = P.dgdtm1; rec[17] = P.r0; rec[18] = P.r; rec[19] = P.r0inv; rec[20] = P.rinv; rec[21] = P.k;
-  rec[22] = P.h; rec[23] = P.beta; rec[24] = P.betainv; rec[25] = P.eta; rec[26] = P.sqb; rec[27] = P.zeta; rec[28] = mi; rec[29] = mj;
-  rec[30] = 0.0; rec[31] = 0.0;
+  rec[6] = P.gamma; rec[7] = P.k; rec[8] = mi; rec[9] = mj; rec[10] = 0.0; rec[11] = 0.0;
 }
-__device__ __forceinline__ void scal_unpack(const double (&rec)[SCF], double* x0, double* v0, KepScal& P, double& mi, double& mj) {
+__device__ __forceinline__ void scal_unpack(const double (&rec)[SCF], double* x0, double* v0, double& gamma, double& k, double& mi, double& mj) {
   x0[0] = rec[0]; x0[1] = rec[1]; x0[2] = rec[2]; v0[0] = rec[3]; v0[1] = rec[4]; v0[2] = rec[5];
-  P.gamma = rec[6]; P.g0 = rec[7]; P.g1 = rec[8]; P.g2 = rec[9]; P.g3 = rec[10]; P.h1 = rec[11]; P.h2 = rec[12]; P.dfdt = rec[13];
-  P.fm1 = rec[14]; P.gmh = rec[15]; P.dgdtm1 = rec[16]; P.r0 = rec[17]; P.r = rec[18]; P.r0inv = rec[19]; P.rinv = rec[20]; P.k = rec[21];
-  P.h = rec[22]; P.beta = rec[23]; P.betainv = rec[24]; P.eta = rec[25]; P.sqb = rec[26]; P.zeta = rec[27]; mi = rec[28]; mj = rec[29];
+  gamma = rec[6]; k = rec[7]; mi = rec[8]; mj = rec[9];
 }
 // The Kepler operator record of one pair section from the pair's Jacobian (jac_ij without its identity, ahl21.jl:735-758):
 // the 6x6 block on relative coordinates, the mass fractions, and the four rank-one mass columns.
