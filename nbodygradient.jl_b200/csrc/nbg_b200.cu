@@ -498,6 +498,9 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     if (s + 1 < nsteps)
       rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
     rx_step<N, U, SYNC, KICK>(S, cur, 0.5 * h, half, c, kmask, hold, NT);
+#ifdef NBG_EXPERIMENTS
+    if (kmask == 0x80000000u) pend = 0u;  // NBG_RX_UNROLL=99, timing experiment only: no transit outputs (the step loop alone)
+#endif
     while (pend != 0u) {  // uniform across the block
       const int body = __ffs(pend) - 1;
       pend &= pend - 1u;
@@ -1402,6 +1405,9 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             if (p->jac_mma == 1) { rc = launch_jac_mma<8, 2, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
             if (p->jac_mma == 2) { rc = launch_jac_mma<8, 2, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
             if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
+            if (p->rx_unroll == 23) { rc = launch_jac_rx<8, 4, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
+            if (p->rx_unroll == 24) { rc = launch_jac_rx<8, 8, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
+            if (p->rx_unroll == 99) { rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O, 0x80000000u); break; }
             if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
 #endif
             // full unroll, no per-group barrier, 2 blocks/SM at 255 registers

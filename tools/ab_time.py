@@ -33,7 +33,7 @@ for r in range(reps + 2):
     L.nbg_last_timings(plan, ptr(kt))
     if r >= 2:
         tot += kt
-print(json.dumps({"lib": lib, "reps": reps, "ms_per_window": {k: round(float(t) / reps, 2) for k, t in
+print(json.dumps({"lib": lib, "reps": reps, "NBG_RX_UNROLL": os.environ.get("NBG_RX_UNROLL"), "ms_per_window": {k: round(float(t) / reps, 2) for k, t in
                   zip(("traj", "transit", "jac", "other", "total", "phi_dense", "pair_op", "adjoint"), tot)},
                   "system_steps_per_s": nsys * window * reps / (tot[4] * 1e-3)}))
 L.nbg_plan_destroy(plan)
