@@ -49,7 +49,7 @@ def f_jac(n):
     return 2744 * n * n * (n - 1) + 392 * n * n * (n - 1) + 168 * n ** 3 + 210 * n * n + 588 * n * n
 
 
-def make_batch(nsys, rank=0):
+def make_elements(nsys, rank=0):
     """cfg 2 ensemble: system b gets elements*(1+1e-4 xi) on m, P; +1e-4 xi on ecosw, esinw, t0; system 0 unperturbed."""
     import nbgrad as nb
     el = nb.trappist1_elements()
@@ -63,6 +63,13 @@ def make_batch(nsys, rank=0):
     elb[:, 1:, 2] += 1e-4 * xi[..., 2]
     elb[:, 1:, 3] += 1e-4 * xi[..., 3]
     elb[:, 1:, 4] += 1e-4 * xi[..., 4]
+    return elb
+
+
+def make_batch(nsys, rank=0):
+    """The ensemble with its host-side initial conditions (x, v, jac_init from the numpy IC layer)."""
+    import nbgrad as nb
+    elb = make_elements(nsys, rank)
     x, v, jac_init = nb.init_nbody_elements(elb, T0)
     return elb, x, v, jac_init
 
@@ -385,7 +392,16 @@ def main():
 
     ngpu = args.gpus if single else 1           # GPUs driven by THIS process
     nsys, window = args.nsys * ngpu, args.window
-    elb, x, v, jac_init = make_batch(nsys, rank)
+    if single:
+        # one process feeding N GPUs: the initial conditions come from the device IC layer (elements in); the numpy IC layer would
+        # spend minutes on a million systems
+        elb = make_elements(nsys, rank)
+        x = v = jac_init = None
+        args.e2e_input, args.no_cpu_baseline = "elements", True
+        if args.e2e_output != "chi2":
+            args.e2e_output = "arrays"
+    else:
+        elb, x, v, jac_init = make_batch(nsys, rank)
     m = np.ascontiguousarray(elb[:, :, 0])
     ntt = ntt_window(window, elb)
     off = np.concatenate([[0], np.cumsum(ntt)[:-1]])
@@ -407,7 +423,11 @@ def main():
         return t, t.numpy()
 
     # ---- device-resident arm ----
-    _lib.check(L.nbg_set_state(plan, ptr(x), ptr(v), ptr(m), C.c_double(T0), None, None, None, None, None))
+    if single:
+        el_dev = np.ascontiguousarray(elb.transpose(0, 2, 1))
+        _lib.check(L.nbg_set_state_elements(plan, ptr(el_dev), None, C.c_double(T0), C.c_int32(0)))
+    else:
+        _lib.check(L.nbg_set_state(plan, ptr(x), ptr(v), ptr(m), C.c_double(T0), None, None, None, None, None))
     tmaxw = window * H
 
     def step_resident():
@@ -461,7 +481,9 @@ def main():
     if not args.no_e2e:
         _lib.check(L.nbg_plan_destroy(plan))
         plan = new_plan()
-        B = dict(x=pin(x)[1], v=pin(v)[1], m=pin(m)[1], j=pin(jac_init.transpose(0, 2, 1))[1], el=pin(elb.transpose(0, 2, 1))[1],
+        zero = np.zeros(1)
+        B = dict(x=pin(x if x is not None else zero)[1], v=pin(v if v is not None else zero)[1], m=pin(m)[1],
+                 j=pin(jac_init.transpose(0, 2, 1) if jac_init is not None else zero)[1], el=pin(elb.transpose(0, 2, 1))[1],
                  tobs=pin(np.full(RT, T0 + 1.0))[1], sig=pin(np.full(RT, 1e-3))[1], chi2=pin(np.zeros(nsys))[1], g=pin(np.zeros((nsys, M)))[1],
                  tt=pin(np.zeros((nsys, RT)))[1], c=pin(np.zeros((nsys, NBODY), dtype=np.int64))[1], d=pin(np.zeros((nsys, RT, M)))[1],
                  e=pin(np.zeros((nsys, RT, M)))[1], xo=pin(np.zeros((nsys, NBODY, 3)))[1], vo=pin(np.zeros((nsys, NBODY, 3)))[1])

@@ -40,6 +40,10 @@
 
 using namespace nbg;
 
+#ifndef NBG_U8
+#define NBG_U8 8   // pivot bodies per block of the pair sweeps of the N = 8 Jacobian kernel (8 = full unroll); -DNBG_U8=4 / 2 for A/B builds
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -1410,8 +1414,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             if (p->rx_unroll == 99) { rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O, 0x80000000u); break; }
             if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
 #endif
-            // full unroll, no per-group barrier, 2 blocks/SM at 255 registers
-            rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O);
+            // NBG_U8 pivot bodies per block of the pair sweeps (8 = full unroll), no per-group barrier, 2 blocks/SM at 255 registers
+            rc = launch_jac_rx<8, NBG_U8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O);
             break;
         }
         if (rc) return fail(NBG_ERR_CUDA, "jac_rx_kernel attribute setup failed");
