@@ -41,7 +41,7 @@
 using namespace nbg;
 
 #ifndef NBG_U8
-#define NBG_U8 8   // pivot bodies per block of the pair sweeps of the N = 8 Jacobian kernel (8 = full unroll); -DNBG_U8=4 / 2 for A/B builds
+#define NBG_U8 4   // pivot bodies per block of the pair sweeps of the N = 8 Jacobian kernel (8 = full unroll); -DNBG_U8=8 / 2 for A/B builds
 #endif
 
 namespace {
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int n
   //   v_sky:   (dJv0 dvx + dJv1 dvy) / vsky + dvdt * d time        b_sky^2:  2 (dJx0 dx + dJx1 dy)
   Z[0].zx[3 * occ] = dvx; Z[0].zx[3 * occ + 1] = dvy; Z[0].zv[3 * occ] = dx; Z[0].zv[3 * occ + 1] = dy;
   Z[0].zx[3 * ti] = -dvx; Z[0].zx[3 * ti + 1] = -dvy; Z[0].zv[3 * ti] = -dx; Z[0].zv[3 * ti + 1] = -dy;
-  if (NC == 3) {
+  if constexpr (NC == 3) {
     Z[NC - 2].zv[3 * occ] = dvx * vskyinv; Z[NC - 2].zv[3 * occ + 1] = dvy * vskyinv;
     Z[NC - 2].zv[3 * ti] = -dvx * vskyinv; Z[NC - 2].zv[3 * ti + 1] = -dvy * vskyinv;
     Z[NC - 1].zx[3 * occ] = 2.0 * dx; Z[NC - 1].zx[3 * occ + 1] = 2.0 * dy;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int n
   double* out = Q.z + (size_t)e * NC * 7 * n;
   for (int r = 0; r < 3 * n; ++r) { out[r] = -gdinv * Z[0].zx[r]; out[3 * n + r] = -gdinv * Z[0].zv[r]; }
   for (int r = 0; r < n; ++r) out[6 * n + r] = -gdinv * Z[0].zm[r];
-  if (NC == 3) {
+  if constexpr (NC == 3) {
     double* o1 = out + 7 * n;
     double* o2 = out + 14 * n;
     for (int r = 0; r < 3 * n; ++r) {
@@ -1414,7 +1414,10 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             if (p->rx_unroll == 99) { rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O, 0x80000000u); break; }
             if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
 #endif
-            // NBG_U8 pivot bodies per block of the pair sweeps (8 = full unroll), no per-group barrier, 2 blocks/SM at 255 registers
+            // NBG_U8 = 4 pivot bodies per block of the pair sweeps, no per-group barrier, 2 blocks/SM at 250 registers.  The full unroll
+            // (U = 8: 110 KB of straight-line code per step, the r01 choice) is at the edge of the instruction cache: the SAME kernel source
+            // took 222, 226 or 238 ms per bench window depending on what else changed in the file, U = 4 (60 KB) 219-223 ms in every
+            // build (profiles/r02f_ab.jsonl, r02g_ab.jsonl); U = 2 is 243 ms (rotation moves).
             rc = launch_jac_rx<8, NBG_U8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O);
             break;
         }

@@ -46,15 +46,13 @@ def block_dev(a, b, n):
     return np.asarray(out)
 
 
-def assert_blocks(name, gpu, ora, exact, n, tol=TOL, loose=None):
+def assert_blocks(name, gpu, ora, exact, n, tol=TOL, guard=10.0):
     """Every block of the GPU result agrees with the Float64 oracle to `tol`, or -- where the reference's own Float64 result is not that
-    good (cancellation-prone blocks) -- is no worse than the oracle measured against the exact (__float128) result:
-    no such block may be off by more than 10 x the oracle's own error, and over those blocks, and over all blocks, the GPU's RMS
-    deviation from the exact result stays within 2 x / 1.5 x the oracle's (per block the two Float64 paths are two realisations of
-    rounding noise, so a per-block factor near 1 cannot be demanded of ~1,000 blocks).
-    loose = (fraction, bound): for dtdelements = dtdq0 . jac_init, whose mass-column blocks cancel by ~1e4: that fraction of the blocks
-    must meet `tol`, every block `bound`, plus the RMS criteria (the reference forms the rows of dtdq0 by differencing rows of jac_step,
-    which is exact for structurally tiny entries; the adjoint route sums products, exact to 1e-16 of the row scale instead)."""
+    good (cancellation-prone blocks: the mass columns of dtdelements = dtdq0 . jac_init cancel by ~1e4, and the oracle itself is up to
+    1e-9 off there) -- is no worse than the oracle measured against the exact (__float128) result: no such block may be off by more than
+    `guard` x the oracle's own error (a lost-cancellation bug showed up as 8,000 x), and over those blocks, and over all blocks, the GPU's
+    RMS deviation from the exact result stays within 2 x / 1.5 x the oracle's.  (Per block the two Float64 paths are two realisations of
+    rounding noise, so a per-block factor near 1 cannot be demanded of ~1,000 blocks.)"""
     eg_o = block_dev(gpu, ora, n)
     if exact is None:
         assert eg_o.max() < tol, "%s: worst block deviation GPU vs oracle %.3e" % (name, eg_o.max())
@@ -62,18 +60,14 @@ def assert_blocks(name, gpu, ora, exact, n, tol=TOL, loose=None):
     eg, eo = block_dev(gpu, exact, n), block_dev(ora, exact, n)
     hard = eg_o >= tol
     rms = lambda a: float(np.sqrt(np.mean(np.square(a)))) if a.size else 0.0
-    if loose is None:
-        ok = ~hard | (eg <= 10.0 * eo + 1e-14)
-        assert ok.all(), "%s: %d of %d blocks fail; worst GPU-vs-oracle %.3e, GPU-vs-exact %.3e where oracle-vs-exact is %.3e" % (
-            name, int((~ok).sum()), ok.size, eg_o[~ok].max(), eg[~ok].max(), eo[~ok][np.argmax(eg[~ok])])
-        assert rms(eg[hard]) <= 2.0 * rms(eo[hard]) + 1e-14, "%s: %d cancellation-prone blocks, RMS deviation from exact GPU %.3e vs oracle %.3e" % (
-            name, int(hard.sum()), rms(eg[hard]), rms(eo[hard]))
-    else:
-        frac, bound = loose
-        assert (~hard).mean() >= frac and eg_o.max() < bound, "%s: %.2f %% of the blocks within %.0e, worst %.3e" % (name, 100 * (~hard).mean(), tol, eg_o.max())
+    print("%s: %d blocks, worst GPU-vs-oracle %.2e (%d above %.0e: RMS deviation from exact GPU %.2e / oracle %.2e); all blocks: GPU %.2e / oracle %.2e" % (
+        name, eg_o.size, eg_o.max(), int(hard.sum()), tol, rms(eg[hard]), rms(eo[hard]), rms(eg), rms(eo)))
+    ok = ~hard | (eg <= guard * eo + 1e-14)
+    assert ok.all(), "%s: %d of %d blocks fail; worst GPU-vs-oracle %.3e, GPU-vs-exact %.3e where oracle-vs-exact is %.3e" % (
+        name, int((~ok).sum()), ok.size, eg_o[~ok].max(), eg[~ok].max(), eo[~ok][np.argmax(eg[~ok])])
+    assert rms(eg[hard]) <= 2.0 * rms(eo[hard]) + 1e-14, "%s: %d cancellation-prone blocks, RMS deviation from exact GPU %.3e vs oracle %.3e" % (
+        name, int(hard.sum()), rms(eg[hard]), rms(eo[hard]))
     assert rms(eg) <= 1.5 * rms(eo) + 1e-15 or rms(eg) < tol, "%s: RMS block deviation from exact GPU %.3e vs oracle %.3e" % (name, rms(eg), rms(eo))
-    print("%s: %d blocks, worst GPU-vs-oracle %.2e (%d above %.0e), RMS deviation from exact GPU %.2e / oracle %.2e" % (
-        name, eg_o.size, eg_o.max(), int(hard.sum()), tol, rms(eg), rms(eo)))
     return eg_o.max()
 
 
@@ -296,8 +290,14 @@ def test_transit_parameters_and_ti(nb, oracle, elements, ti):
     assert rel(tp.ttbv[0, 1], r["tt"][1]) < TOL                      # v_sky
     assert np.max(np.abs(tp.ttbv[0, 2] - r["tt"][2])) < 1e-11 * 1e-4  # b_sky^2 ~ 0 for this edge-on system: absolute
     assert rel(tp.dtbvdq0[0, 0], r["dtdq0"][0]) < TOL
-    assert rel(tp.dtbvdq0[0, 1], r["dtdq0"][1]) < TOL
-    assert rel(tp.dtbvdelements[0, :2], r["dtdelements"][:2]) < TOL
+    # ti = 1 (a planet as the "transited" body) also catches g = 0 events that are stationary points of the relative sky motion of two
+    # planets, not conjunctions: v_sky = 1e-18 there (body 2, fourth event), its gradient is 0/0 and depends on the last bit of the
+    # converged time in the reference as much as here.  Those rows are compared for the time component only.
+    good = r["tt"][1] > 1e-6
+    assert good.sum() >= r["count"].sum() - 1
+    assert rel(np.where(good[..., None, None], tp.dtbvdq0[0, 1], 0.0), np.where(good[..., None, None], r["dtdq0"][1], 0.0)) < TOL
+    assert rel(tp.dtbvdelements[0, 0], r["dtdelements"][0]) < TOL
+    assert rel(np.where(good[..., None, None], tp.dtbvdelements[0, 1], 0.0), np.where(good[..., None, None], r["dtdelements"][1], 0.0)) < TOL
 
 
 def test_outer_solar_system_nograd_energy(nb, oracle):
@@ -796,7 +796,7 @@ def test_block_scaled_parity(nb, oracle, elements):
         _cmp_tt(tt.tt[0], tt.count[0], r)
         w = [assert_blocks("jac_step", s.jac_step[0], so["jac_step_cm"].T, q["jac_step_cm"].T, n),
              assert_blocks("dtdq0", tt.dtdq0[0], r["dtdq0"], q["dtdq0"], n),
-             assert_blocks("dtdelements", tt.dtdelements[0], r["dtdelements"], q["dtdelements"], n, loose=(0.99, 1e-10))]
+             assert_blocks("dtdelements", tt.dtdelements[0], r["dtdelements"], q["dtdelements"], n, guard=30.0)]
         print("trial %d: worst block deviation GPU vs oracle: jac_step %.2e, dtdq0 %.2e, dtdelements %.2e" % ((trial,) + tuple(w)))
     # cfg 1 flavour (3 bodies, planets x100, tilted): blocks of the propagated Jacobian and of dq/dh
     el = elements[:3].copy(); el[1, 0] *= 100; el[2, 0] *= 100; el[:, 6] = 0
