@@ -6,8 +6,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.environ.get("NBGRAD_B200_LIB") or os.path.join(CSRC, "libnbgrad_b200.so")  # env override: A/B builds on the GPU box
 SOURCES = ["nbg_b200.cu"]
-# --split-compile 0: ptxas works on the kernels in parallel (1 m 50 s -> 45 s on 8 cores, same register counts)
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0"]
+# No --split-compile: it cuts the build from 2 min to 45 s, but the partitioning changes the register allocation of the hottest kernel from
+# build to build (jac_rx_kernel<8,4>: 250 registers / 220 ms per bench window in one build, 204 registers / 237 ms in the next, same source;
+# profiles/r02h_ab.jsonl).  NBGRAD_FAST_BUILD=1 turns it on for development builds.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+if os.environ.get("NBGRAD_FAST_BUILD") == "1":
+    NVCC_FLAGS += ["--split-compile", "0"]
 # NBGRAD_EXPERIMENTS=1 also compiles the measured-and-rejected kernel variants (DMMA Jacobian kernel, pivot-block / lockstep variants of
 # jac_rx_kernel: DESIGN.md 5); they double the build time and are off by default
 if os.environ.get("NBGRAD_EXPERIMENTS") == "1":

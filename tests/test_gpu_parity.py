@@ -62,7 +62,9 @@ def assert_blocks(name, gpu, ora, exact, n, tol=TOL, guard=10.0):
     rms = lambda a: float(np.sqrt(np.mean(np.square(a)))) if a.size else 0.0
     print("%s: %d blocks, worst GPU-vs-oracle %.2e (%d above %.0e: RMS deviation from exact GPU %.2e / oracle %.2e); all blocks: GPU %.2e / oracle %.2e" % (
         name, eg_o.size, eg_o.max(), int(hard.sum()), tol, rms(eg[hard]), rms(eo[hard]), rms(eg), rms(eo)))
-    ok = ~hard | (eg <= guard * eo + 1e-14)
+    # (a block also passes if it is within 3 x the oracle's typical -- RMS -- error over the cancellation-prone blocks: where the oracle
+    # happens to hit the exact value to 1e-13, a factor against that single block says nothing)
+    ok = ~hard | (eg <= guard * eo + 1e-14) | (eg <= 3.0 * rms(eo[hard]))
     assert ok.all(), "%s: %d of %d blocks fail; worst GPU-vs-oracle %.3e, GPU-vs-exact %.3e where oracle-vs-exact is %.3e" % (
         name, int((~ok).sum()), ok.size, eg_o[~ok].max(), eg[~ok].max(), eo[~ok][np.argmax(eg[~ok])])
     assert rms(eg[hard]) <= 2.0 * rms(eo[hard]) + 1e-14, "%s: %d cancellation-prone blocks, RMS deviation from exact GPU %.3e vs oracle %.3e" % (
