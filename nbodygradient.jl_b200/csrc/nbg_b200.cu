@@ -463,7 +463,9 @@ __device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQ
   }
 }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
+// DBUF = false (N = 15, 16): ONE operator buffer (129 / 147 KB; two do not fit in 227 KB): the next step's block is fetched after the step
+// instead of under it -- a few microseconds per step exposed, against the shared-memory kernel that is 4-5 x slower at these sizes.
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, bool DBUF = true>
 __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, size_t ld, const double* __restrict__ stream, int nsteps, double h,
                   const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O, uint32_t kmask, long nsys) {
@@ -473,8 +475,9 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
                 SB = 2 * P * KF + NS * 12 * N * N /* staged */, G0 = 2 * P * KF / 4, GSKIP = P * (2 * KF + NS * PF) / 4, G1 = NS * 3 * N * N,
                 NT = rx_warps(N) * 32;
   const int tid = (int)threadIdx.x;
-  double* const hold = smrx + 2 * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
-  double* const acc = smrx + 2 * SB + (KICK ? 3 * N * NT : 0);  // fused chi^2: NT gradient accumulators + the chi^2 sum of this chunk
+  constexpr int NBUF = DBUF ? 2 : 1;
+  double* const hold = smrx + NBUF * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
+  double* const acc = smrx + NBUF * SB + (KICK ? 3 * N * NT : 0);  // fused chi^2: NT gradient accumulators + the chi^2 sum of this chunk
   const long sys = blockIdx.x;
   if (sys >= nsys) return;
   acc[tid] = 0.0;
@@ -491,15 +494,19 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
       S.je[b][k] = valid ? Je_g[q] : 0.0;
     }
   double* const buf0 = smrx;
-  double* const buf1 = smrx + SB;
+  double* const buf1 = smrx + (DBUF ? SB : 0);
   const size_t ntiles = ld / TILE;
   if (nsteps > 0) rx_fetch(buf0, stream + tile_offset(SFS, ntiles, 0, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
   for (int s = 0; s < nsteps; ++s) {
     double* const cur = (s & 1) ? buf1 : buf0;
     uint32_t pend = evmask ? evmask[(size_t)s * ld + sys] : 0u;   // bodies with a queued transit at the end of step s
+    if (!DBUF && s > 0) {   // single buffer: everyone is done with step s-1 (and its transits); fetch step s now
+      __syncthreads();
+      rx_fetch(buf0, stream + tile_offset(SFS, ntiles, (size_t)s, (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
+    }
     __pipeline_wait_prior(0);
     __syncthreads();  // step s operators visible; everyone is done with the other buffer
-    if (s + 1 < nsteps)
+    if (DBUF && s + 1 < nsteps)
       rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
     rx_step<N, U, SYNC, KICK>(S, cur, 0.5 * h, half, c, kmask, hold, NT);
 #ifdef NBG_EXPERIMENTS
@@ -732,15 +739,15 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
   return 0;
 }
 
-template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false>
+template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, bool DBUF = true>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h, const int32_t* evlist,
                   const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
-  const size_t smem = ((size_t)2 * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0) + rx_warps(N) * 32 + 1) * 8;
+  const size_t smem = ((size_t)(DBUF ? 2 : 1) * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0) + rx_warps(N) * 32 + 1) * 8;
   // per launch, not once: function attributes are per device, and plans of one process may live on different devices
-  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  jac_rx_kernel<N, U, SYNC, MB, KICK><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask, nsys);
+  if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, DBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, DBUF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  jac_rx_kernel<N, U, SYNC, MB, KICK, DBUF><<<(unsigned)nsys, rx_warps(N) * 32, smem, st>>>(Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask, nsys);
   return 0;
 }
 // fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
@@ -1402,6 +1409,8 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
           case 12: rc = launch_jac_rx<12, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 13: rc = launch_jac_rx<13, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
           case 14: rc = launch_jac_rx<14, 1, true, 1>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
+          case 15: rc = launch_jac_rx<15, 1, true, 1, false, false>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;   // single operator buffer
+          case 16: rc = launch_jac_rx<16, 1, true, 1, false, false>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break;
           default:
 #ifdef NBG_EXPERIMENTS
             // measured and rejected: the DMMA kernel, pivot blocks of 2 with a barrier per group (22), pivot blocks of 2 at

@@ -26,7 +26,7 @@
 namespace nbg {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int NBG_RX_MAX_BODIES = 14;  // largest N with jac_step + jac_error in registers and a double-buffered operator block in shared memory
+constexpr int NBG_RX_MAX_BODIES = 16;  // jac_step + jac_error in registers; the operator block in shared memory is double-buffered for N <= 14, single for 15, 16
 __host__ __device__ constexpr int rx_warps(int n) { return (7 * n + 15) / 16; }
 
 __device__ __forceinline__ double shx(double v) { return __shfl_xor_sync(FULL, v, 16); }
