@@ -72,7 +72,7 @@ def run_cfg4(L, n, nsys, steps, peak, generic=False, variant=None):
     L.nbg_plan_destroy(plan)
     rate = nsys * steps / (best[4] * 1e-3)
     tf = rate * f_grad(n) / 1e12
-    return {"config": "cfg4", "nbody": n, "variant": variant, "batch": nsys, "steps": steps, "jacobian_kernel": "shared-memory (generic)" if (generic or n > 14) else "register-resident",
+    return {"config": "cfg4", "nbody": n, "variant": variant, "batch": nsys, "steps": steps, "jacobian_kernel": "shared-memory (generic)" if generic else ("register-resident" if n <= 14 else "register-resident, single operator buffer"),
             "device_ms": float(best[4]), "system_steps_per_s": rate, "canonical_tflops": tf, "frac_fp64_peak": tf / peak if peak else None,
             "kernel_ms": {"traj": float(best[0]), "jac": float(best[2]), "phi_dense": float(best[5]), "pair_op": float(best[6])},
             "nonfinite": int((status & 1 != 0).sum())}
