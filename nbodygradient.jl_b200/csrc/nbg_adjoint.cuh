@@ -122,9 +122,9 @@ __device__ __forceinline__ void adj_dense(AdjVec<NMAX> (&Z)[NC], const Src& S, s
 
 // z = T^T w for the NC output components of one queued transit.  blk: the transit's operator block in the tiled stream.
 template <int NC>
-__device__ __forceinline__ void adjoint_step(AdjVec<NMAX> (&Z)[NC], const Src& S, int n, double h2, uint32_t kmask) {
+__device__ __forceinline__ void adjoint_step(AdjVec<NMAX> (&Z)[NC], const Src& S, int n, double h2, const KMask& kmask) {
   const int P = npairs(n);
-  const bool kicks = kmask != 0u;
+  const bool kicks = kmask.any();
   auto drift_t = [&]() {
 #pragma unroll
     for (int q = 0; q < NC; ++q)
@@ -137,14 +137,14 @@ __device__ __forceinline__ void adjoint_step(AdjVec<NMAX> (&Z)[NC], const Src& S
     int rec = 2 * P - 1;
     for (int i = 0; i <= n - 2; ++i)
       for (int j = i + 1; j <= n - 1; ++j, --rec)
-        if (!kicks || !((kmask >> rx_pair_index(n, i, j)) & 1u)) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
+        if (!kicks || !kmask.bit(rx_pair_index(n, i, j))) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
   }
   adj_dense<NC>(Z, S, phi_dense_offset(n, kicks, kicks ? 1 : 0), n, 0.0, false);   // phic! + phisalpha!
   {  // ascending sweep reversed
     int rec = P - 1;
     for (int i = n - 2; i >= 0; --i)
       for (int j = n - 1; j >= i + 1; --j, --rec)
-        if (!kicks || !((kmask >> rx_pair_index(n, i, j)) & 1u)) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
+        if (!kicks || !kmask.bit(rx_pair_index(n, i, j))) adj_pair<NC>(Z, S, (size_t)rec * KF, i, j);
   }
   if (kicks) adj_dense<NC>(Z, S, phi_dense_offset(n, true, 0), n, h2, true);       // first kickfast! + drift (quirk B-3)
   else drift_t();

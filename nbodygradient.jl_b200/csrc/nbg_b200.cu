@@ -99,7 +99,7 @@ __device__ __forceinline__ size_t out_rec(const TransitOut& O, long sys, int bod
 template <bool GRAD, int EMIT, bool KICKS = false>
 __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel(TrajArrays T, int n, long nsys, double h, int nsteps, double* stream, double* scal, int detect, int ti,
                                                    double t0, long istep0, double h_intr, const int32_t* ntt_body, EventQueue Q,
-                                                   int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err, uint32_t kmask) {
+                                                   int32_t* evlist, uint32_t* evmask, int time_mode_kahan, double* tkahan_err, KMask kmask) {
   const long sys = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= nsys) return;
   const size_t ld = T.ld;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128, (EMIT == 2 && !GRAD) ? 4 : 1) traj_kernel
   if (detect) for (int i = 0; i < n; ++i) { gs[i] = T.gsave[i * ld + sys]; cnt[i] = T.count[i * ld + sys]; }
   double tnow = T.t[sys], terr = tkahan_err ? tkahan_err[sys] : 0.0;
   uint32_t st = 0;
-  const size_t sf = step_fields(n, kmask != 0u);
+  const size_t sf = step_fields(n, kmask.any());
   for (int s = 0; s < nsteps; ++s) {
     if (T.samp_x && (istep0 + s) % T.samp_stride == 0) {  // o.states[i] = deepcopy(s) before the step (Outputs.jl:40)
       const size_t k = (size_t)((istep0 + s) / T.samp_stride);
@@ -193,7 +193,7 @@ __global__ void gsave_init_kernel(TrajArrays T, int n, long nsys, int ti) {
 // One gradient-free AHL21 step followed by the Newton correction -g / (dg/dt along the flow): kept out of line so that the
 // reference-form iterations of transit_kernel compile exactly as they do without it.
 template <bool KICKS>
-__device__ __noinline__ double transit_pre_iteration(const Body& b0, int n, double dt0, int ti, int j, uint32_t kmask) {
+__device__ __noinline__ double transit_pre_iteration(const Body& b0, int n, double dt0, int ti, int j, const KMask& kmask) {
   Body b = b0;
   Emit none{nullptr, 0, 0};
   ahl21_step<false, 0, KICKS>(b, nullptr, n, dt0, none, kmask);
@@ -204,7 +204,7 @@ __device__ __noinline__ double transit_pre_iteration(const Body& b0, int n, doub
 // findtransit! (timing.jl:31-110).  One thread per queued transit.
 // (capping the registers for 3 / 4 blocks per SM was measured: 167 -> 198 / 206 ms per 3 bench steps, the spills cost more than the warps hide)
 template <bool GRAD, bool KICKS = false>
-__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, uint32_t kmask, int npre) {
+__global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, EventQueue Q, int ti, TransitOut O, unsigned long long* counters, KMask kmask, int npre) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = min(*Q.n, Q.cap);
   if (e >= nq) return;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
   // dt0 == tt1 it repeats the last iteration bit for bit and could be skipped by emitting records inside the loop; measured on
   // B200 that is slower -- 72 vs 65 ms per bench step for this kernel with full records, 69 with only the 14 KB of scalars that
   // pair_op_kernel needs -- the iterations, already at 255 registers with spills, get slower by more than the saved step.)
-  Emit em{GRAD ? Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e) : nullptr, TILE, (size_t)(e % TILE)};
+  Emit em{GRAD ? Q.stream + tile_offset(step_fields(n, kmask.any()), 0, 0, (size_t)e) : nullptr, TILE, (size_t)(e % TILE)};
   while (true) {
     tt2 = tt1;
     tt1 = dt0;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(128) transit_kernel(TrajArrays T, int n, Event
 // phi_dense_kernel) and the header (sky-plane separations, 1/gdot, ...); writes z scaled so that the Jacobian kernel's dot product
 // IS the output:  out_c[col] = z_c^T J[:, col] (+ zm of the body whose mass column it is).
 template <int NC>
-__global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int nq, int n, int ti, uint32_t kmask) {
+__global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int nq, int n, int ti, KMask kmask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nq) return;
   const size_t cap = Q.cap;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int n
     Z[NC - 1].zx[3 * occ] = 2.0 * dx; Z[NC - 1].zx[3 * occ + 1] = 2.0 * dy;
     Z[NC - 1].zx[3 * ti] = -2.0 * dx; Z[NC - 1].zx[3 * ti + 1] = -2.0 * dy;
   }
-  const Src S{Q.stream + tile_offset(step_fields(n, kmask != 0u), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
+  const Src S{Q.stream + tile_offset(step_fields(n, kmask.any()), 0, 0, (size_t)e), TILE, (size_t)(e % TILE)};
   adjoint_step<NC>(Z, S, n, 0.5 * dt0, kmask);
   double* out = Q.z + (size_t)e * NC * 7 * n;
   for (int r = 0; r < 3 * n; ++r) { out[r] = -gdinv * Z[0].zx[r]; out[3 * n + r] = -gdinv * Z[0].zv[r]; }
@@ -465,10 +465,16 @@ __device__ __forceinline__ void rx_transit_out(const RxState<N>& S, const EventQ
 
 // DBUF = false (N = 15, 16): ONE operator buffer (129 / 147 KB; two do not fit in 227 KB): the next step's block is fetched after the step
 // instead of under it -- a few microseconds per step exposed, against the shared-memory kernel that is 4-5 x slower at these sizes.
+// shared memory of the fast-kick variant: operator buffer(s) with three dense operators, + the per-thread scratch of the first kick if it fits
+__host__ __device__ constexpr size_t rx_kick_staged(int n) { return (size_t)n * (n - 1) * KF + (size_t)3 * 12 * n * n; }
+__host__ __device__ constexpr bool rx_kick_dbuf(int n) { return (2 * rx_kick_staged(n) + (size_t)3 * n * rx_warps(n) * 32 + rx_warps(n) * 32 + 1) * 8 <= (size_t)227 * 1024; }
+__host__ __device__ constexpr bool rx_kick_hold_fits(int n, bool dbuf) {
+  return ((dbuf ? 2 : 1) * rx_kick_staged(n) + (size_t)3 * n * rx_warps(n) * 32 + rx_warps(n) * 32 + 1) * 8 <= (size_t)227 * 1024;
+}
 template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, bool DBUF = true>
 __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     jac_rx_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, size_t ld, const double* __restrict__ stream, int nsteps, double h,
-                  const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O, uint32_t kmask, long nsys) {
+                  const int32_t* __restrict__ evlist, const uint32_t* __restrict__ evmask, EventQueue Q, int ti, TransitOut O, KMask kmask, long nsys) {
   extern __shared__ __align__(16) double smrx[];
   constexpr int NS = KICK ? 3 : 1;  // dense operators per step (nbg_kicks.cuh)
   constexpr int M = 7 * N, P = N * (N - 1) / 2, SFS = P * (2 * KF + NS * PF) + NS * 12 * N * N /* stream */,
@@ -476,8 +482,13 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
                 NT = rx_warps(N) * 32;
   const int tid = (int)threadIdx.x;
   constexpr int NBUF = DBUF ? 2 : 1;
-  double* const hold = smrx + NBUF * SB + threadIdx.x;  // KICK only: 3N doubles per thread, stride NT
-  double* const acc = smrx + NBUF * SB + (KICK ? 3 * N * NT : 0);  // fused chi^2: NT gradient accumulators + the chi^2 sum of this chunk
+  // KICK only: 3N doubles per thread for the first kickfast! (rx_phisalpha_dense HOLD): in shared memory with stride NT, or, where the
+  // operator buffer leaves no room for them (N = 15, 16), in local memory
+  constexpr bool HOLD_LOCAL = KICK && !rx_kick_hold_fits(N, DBUF);
+  double hold_l[HOLD_LOCAL ? 3 * N : 1];
+  double* const hold = HOLD_LOCAL ? hold_l : smrx + NBUF * SB + threadIdx.x;
+  constexpr int HS = HOLD_LOCAL ? 1 : NT;
+  double* const acc = smrx + NBUF * SB + (KICK && !HOLD_LOCAL ? 3 * N * NT : 0);  // fused chi^2: NT gradient accumulators + the chi^2 sum of this chunk
   const long sys = blockIdx.x;
   if (sys >= nsys) return;
   acc[tid] = 0.0;
@@ -508,9 +519,9 @@ __global__ void __launch_bounds__(rx_warps(N) * 32, MB)
     __syncthreads();  // step s operators visible; everyone is done with the other buffer
     if (DBUF && s + 1 < nsteps)
       rx_fetch((s & 1) ? buf0 : buf1, stream + tile_offset(SFS, ntiles, (size_t)(s + 1), (size_t)sys), TILE, (size_t)(sys % TILE), G0, GSKIP, G1, tid, NT);
-    rx_step<N, U, SYNC, KICK>(S, cur, 0.5 * h, half, c, kmask, hold, NT);
+    rx_step<N, U, SYNC, KICK>(S, cur, 0.5 * h, half, c, kmask, hold, HS);
 #ifdef NBG_EXPERIMENTS
-    if (kmask == 0x80000000u) pend = 0u;  // NBG_RX_UNROLL=99, timing experiment only: no transit outputs (the step loop alone)
+    if (kmask.w[3] == 0x80000000u) pend = 0u;  // NBG_RX_UNROLL=99, timing experiment only: no transit outputs (the step loop alone)
 #endif
     while (pend != 0u) {  // uniform across the block
       const int body = __ffs(pend) - 1;
@@ -675,7 +686,7 @@ __global__ void __launch_bounds__(32 * N, 512 / (32 * N)) phi_dense_kernel(doubl
   if (idx >= nv) return;
   double* blk = base + tile_offset(step_fields(N, kicked != 0), ntiles, blockIdx.y, (size_t)idx);
   if (!kicked) phi_dense_rows<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y);
-  else if constexpr (N <= 8)  // fast-kick pairs exist for N <= 8 only (pair mask in 32 bits)
+  else
     phi_dense_rows_kicked<N>(blk, TILE, (size_t)threadIdx.x, (int)threadIdx.y, phi_rec_offset(N, blockIdx.z), phi_dense_offset(N, true, blockIdx.z));
 }
 // the same (no fast-kick pairs) with the per-pair tensors cached in shared memory (phi_dense_rows_cached): FULL for N <= 10
@@ -741,9 +752,9 @@ int launch_phi_dense(cudaStream_t st, int n, double* base, size_t ntiles, long n
 
 template <int N, int U, bool SYNC = true, int MB = rx_minblocks<N>(), bool KICK = false, bool DBUF = true>
 int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h, const int32_t* evlist,
-                  const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask = 0u) {
+                  const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, const KMask& kmask = KMask{}) {
   constexpr int P = N * (N - 1) / 2, NS = KICK ? 3 : 1, SB = 2 * P * KF + NS * 12 * N * N;
-  const size_t smem = ((size_t)(DBUF ? 2 : 1) * SB + (KICK ? (size_t)3 * N * rx_warps(N) * 32 : 0) + rx_warps(N) * 32 + 1) * 8;
+  const size_t smem = ((size_t)(DBUF ? 2 : 1) * SB + (KICK && rx_kick_hold_fits(N, DBUF) ? (size_t)3 * N * rx_warps(N) * 32 : 0) + rx_warps(N) * 32 + 1) * 8;
   // per launch, not once: function attributes are per device, and plans of one process may live on different devices
   if (cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, DBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   cudaFuncSetAttribute(jac_rx_kernel<N, U, SYNC, MB, KICK, DBUF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -752,7 +763,7 @@ int launch_jac_rx(cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld,
 }
 // fast-kick pairs: one generic variant per N (pivot blocks of 1, one block per SM)
 int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* Je, size_t ld, const double* stream, int nsteps, double h,
-                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, uint32_t kmask) {
+                         const int32_t* evlist, const uint32_t* evmask, const EventQueue& Q, int ti, const TransitOut& O, const KMask& kmask) {
   switch (n) {
     case 2: return launch_jac_rx<2, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
     case 3: return launch_jac_rx<3, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
@@ -761,6 +772,15 @@ int launch_jac_rx_kicked(int n, cudaStream_t st, long nsys, double* Jv, double* 
     case 6: return launch_jac_rx<6, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
     case 7: return launch_jac_rx<7, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
     case 8: return launch_jac_rx<8, 1, true, 1, true>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    // N > 8: two operator buffers while they fit (N <= 11), then one; N = 15, 16 keep the first kick's scratch in local memory
+    case 9: return launch_jac_rx<9, 1, true, 1, true, rx_kick_dbuf(9)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 10: return launch_jac_rx<10, 1, true, 1, true, rx_kick_dbuf(10)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 11: return launch_jac_rx<11, 1, true, 1, true, rx_kick_dbuf(11)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 12: return launch_jac_rx<12, 1, true, 1, true, rx_kick_dbuf(12)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 13: return launch_jac_rx<13, 1, true, 1, true, rx_kick_dbuf(13)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 14: return launch_jac_rx<14, 1, true, 1, true, rx_kick_dbuf(14)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 15: return launch_jac_rx<15, 1, true, 1, true, rx_kick_dbuf(15)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
+    case 16: return launch_jac_rx<16, 1, true, 1, true, rx_kick_dbuf(16)>(st, nsys, Jv, Je, ld, stream, nsteps, h, evlist, evmask, Q, ti, O, kmask);
   }
   return -1;
 }
@@ -981,7 +1001,7 @@ struct nbg_plan {
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tev;  // timing events, created once and reused by every call (Timer)
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true, overlap3 = false;
-  uint32_t kmask = 0;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
+  KMask kmask;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
   int phi_cached = 2;  // NBG_PHI_CACHED: 0 = phi_dense_kernel without the shared-memory cache of the per-pair tensors, 1 = T / gam cached, 2 = all pair fields
   int jac_mma = 0;     // NBG_JAC_MMA (NBG_EXPERIMENTS builds only): DMMA Jacobian kernel for N = 8, measured 12-18 % slower than jac_rx_kernel
@@ -1148,7 +1168,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   const long nsys = p->nsys;
   const size_t ld = p->ld;
   const size_t M = 7 * (size_t)n, C = p->C;
-  const bool kicks = p->kmask != 0u;
+  const bool kicks = p->kmask.any();
   const size_t sf = step_fields(n, kicks);
   const bool rows = detect && p->sink.active;            // per-chunk event rows, streamed to the host
   const bool fused = detect && grad && p->fused;        // chi^2 gradient accumulated in the Jacobian kernel
@@ -1215,7 +1235,6 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
     evmask = p->bevmask.as<uint32_t>();
   }
   const bool use_rx = n <= NBG_RX_MAX_BODIES && (!p->force_generic_jac || kicks);
-  if (kicks && n > 8) return fail(NBG_ERR_UNSUPPORTED, "fast-kick pairs (s.pair) are supported for nbody <= 8");
   const int tpb = 128;
   const unsigned gridA = (unsigned)((nsys + tpb - 1) / tpb);
   const int tps = 32 * ((7 * n + 31) / 32);
@@ -1420,7 +1439,7 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
             if (p->rx_unroll == 22) { rc = launch_jac_rx<8, 2, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
             if (p->rx_unroll == 23) { rc = launch_jac_rx<8, 4, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
             if (p->rx_unroll == 24) { rc = launch_jac_rx<8, 8, true, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
-            if (p->rx_unroll == 99) { rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O, 0x80000000u); break; }
+            if (p->rx_unroll == 99) { KMask notr; notr.w[3] = 0x80000000u; rc = launch_jac_rx<8, 8, false, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O, notr); break; }
             if (p->rx_unroll != 38) { rc = launch_jac_rx<8, 2>(st, nsys, Jv, Je, ld, strm, s, h, evl, evm, Q, ti, O); break; }
 #endif
             // NBG_U8 = 4 pivot bodies per block of the pair sweeps, no per-group barrier, 2 blocks/SM at 250 registers.  The full unroll
@@ -1476,17 +1495,12 @@ int ensure_jac(nbg_plan* p) {
 }
 
 // s.pair (Integrator.jl:91): Julia column-major N x N Bool, entry [i,j] at i + n*j; the reference only reads i < j
-int pair_mask(const uint8_t* pair, int n, uint32_t* mask) {
-  *mask = 0;
+int pair_mask(const uint8_t* pair, int n, KMask* mask) {
+  *mask = KMask{};
   if (!pair) return 0;
-  bool any = false;
   for (int i = 0; i < n - 1; ++i)
     for (int j = i + 1; j < n; ++j)
-      if (pair[i + n * j]) {
-        any = true;
-        if (n <= 8) *mask |= 1u << (i * n - i * (i + 1) / 2 + (j - i - 1));
-      }
-  if (any && n > 8) return fail(NBG_ERR_UNSUPPORTED, "fast-kick pairs (s.pair) are supported for nbody <= 8");
+      if (pair[i + n * j]) mask->set(i * n - i * (i + 1) / 2 + (j - i - 1));
   return 0;
 }
 
@@ -1687,7 +1701,7 @@ int32_t nbg_set_pair(nbg_plan* p, const uint8_t* pair) {
     for (nbg_plan* k : p->kids) if (int r = nbg_set_pair(k, pair)) return r;
     return NBG_OK;
   }
-  uint32_t mask = 0;
+  KMask mask;
   if (int r = pair_mask(pair, p->n, &mask)) return r;
   p->kmask = mask;
   return NBG_OK;

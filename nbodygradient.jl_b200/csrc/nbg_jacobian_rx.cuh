@@ -618,13 +618,13 @@ template <int N, int U, bool SYNC = true> struct RxSweep {
 // KICK: fast-kick pairs present (kmask, nbg_kicks.cuh): three dense operators (kickfast!, phic!+phisalpha!, kickfast!), the
 // flagged pairs are skipped in the Kepler sweeps; hold/hs: per-thread scratch for the first kick (see rx_phisalpha_dense).
 template <int N, int U, bool SYNC = true, bool KICK = false>
-__device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c, uint32_t kmask = 0u,
+__device__ __forceinline__ void rx_step(RxState<N>& S, const double* __restrict__ blk, double h2, int half, int c, const KMask& kmask = KMask{},
                                         double* hold = nullptr, int hs = 0) {
   constexpr int P = N * (N - 1) / 2, DF = 12 * N * N;
   using SW = RxSweep<N, U, SYNC>;
   auto rotate = [&](auto Kc) { rot_left_by<N, decltype(Kc)::value>(S.jv); rot_left_by<N, decltype(Kc)::value>(S.je); };
   auto pair = [&](auto PA, auto PB, const double* R, int bi, int bj) {
-    if (!KICK || !((kmask >> rx_pair_index(N, bi, bj)) & 1u)) rx_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, half, c, 7 * bi + 6, 7 * bj + 6);
+    if (!KICK || !kmask.bit(rx_pair_index(N, bi, bj))) rx_pair<N, decltype(PA)::value, decltype(PB)::value>(S, R, half, c, 7 * bi + 6, 7 * bj + 6);
   };
   const double* __restrict__ D = blk + 2 * P * KF;
   if (KICK) rx_phisalpha_dense<N, 0, true>(S, D, half, c, hold, hs);

@@ -21,11 +21,11 @@ namespace nbg {
 constexpr int PF_KAPPA = 22;
 constexpr int PF_CLASS = 23;
 
-__device__ __forceinline__ bool kicked(uint32_t kmask, int p) { return p < 32 && ((kmask >> p) & 1u); }
+__device__ __forceinline__ bool kicked(const KMask& kmask, int p) { return kmask.bit(p); }
 
 // kickfast!(s,d,hk) over the flagged pairs.  first: the call at the start of the step (dq/dh is still zero there, ahl21.jl:9-14).
 template <bool GRAD, int EMIT>
-__device__ __forceinline__ void kick_section(Body& b, double* dq, int n, double hk, uint32_t kmask, bool first, const Emit& em, size_t pf_base) {
+__device__ __forceinline__ void kick_section(Body& b, double* dq, int n, double hk, const KMask& kmask, bool first, const Emit& em, size_t pf_base) {
   double dvacc[3 * NMAX];
   if (GRAD) for (int q = 0; q < 3 * n; ++q) dvacc[q] = 0.0;
   int p = 0;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void kick_section(Body& b, double* dq, int n, double 
 // phic!(s,d,h) over the flagged pairs followed by phisalpha!(s,d,h,2) over the others; both add into the same jac_phi /
 // dqdt_phi in the reference (ahl21.jl:46-54), so one dense operator describes them.
 template <bool GRAD, int EMIT>
-__device__ __forceinline__ void phi_kicked_section(Body& b, double* dq, int n, double h, uint32_t kmask, const Emit& em, size_t pf_base) {
+__device__ __forceinline__ void phi_kicked_section(Body& b, double* dq, int n, double h, const KMask& kmask, const Emit& em, size_t pf_base) {
   double a[3 * NMAX], da[3 * NMAX], dvacc[3 * NMAX];
   if (GRAD) for (int q = 0; q < 3 * n; ++q) dvacc[q] = 0.0;
 #pragma unroll 1
@@ -212,18 +212,18 @@ __device__ __forceinline__ void phi_kicked_section(Body& b, double* dq, int n, d
 // kmask: bit p set = pair p (rx_pair_index order) is a fast-kick pair (s.pair[i,j]); 0 = the reference default.
 // KICKS = false compiles the fast-kick branches out (the default path pays nothing for them).
 template <bool GRAD, int EMIT, bool KICKS = false>
-__device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em, uint32_t kmask_in = 0u) {
-  const uint32_t kmask = KICKS ? kmask_in : 0u;
+__device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em, const KMask& kmask = KMask{}) {
+  const bool kicks = KICKS && kmask.any();
   const double h2 = 0.5 * h;
   const int P = npairs(n);
   // fill!(s.dqdt,0); kickfast!; drift_grad!/drift!; dqdt[x] = v/2 + h2 dqdt[v]   (ahl21.jl:8-21)
-  if (kmask) kick_section<GRAD, EMIT>(b, dq, n, h / 6.0, kmask, true, em, phi_rec_offset(n, 0));
+  if (kicks) kick_section<GRAD, EMIT>(b, dq, n, h / 6.0, kmask, true, em, phi_rec_offset(n, 0));
   for (int i = 0; i < n; ++i) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       ksum(b.x[3 * i + k], b.xe[3 * i + k], h2 * b.v[3 * i + k]);
       if (GRAD) {
-        if (kmask) dq[6 * i + k] = 0.5 * b.v[3 * i + k] + h2 * dq[6 * i + 3 + k];
+        if (kicks) dq[6 * i + k] = 0.5 * b.v[3 * i + k] + h2 * dq[6 * i + 3 + k];
         else { dq[6 * i + k] = 0.5 * b.v[3 * i + k]; dq[6 * i + 3 + k] = 0.0; }
       }
     }
@@ -236,12 +236,12 @@ __device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em,
     for (int j = i + 1; j < n; ++j, ++rec) {
       bj = bn;
       if (j + 1 < n) load_body<GRAD>(b, dq, j + 1, bn);  // in flight while pair (i, j) is solved
-      if (!kicked(kmask, rec)) pair_section<GRAD, EMIT>(bi, bj, h2, true, em, (size_t)rec * KF);
+      if (!kicks || !kicked(kmask, rec)) pair_section<GRAD, EMIT>(bi, bj, h2, true, em, (size_t)rec * KF);
       store_body<GRAD>(b, dq, j, bj);
     }
     store_body<GRAD>(b, dq, i, bi);
   }
-  if (kmask) phi_kicked_section<GRAD, EMIT>(b, dq, n, h, kmask, em, phi_rec_offset(n, 1));
+  if (kicks) phi_kicked_section<GRAD, EMIT>(b, dq, n, h, kmask, em, phi_rec_offset(n, 1));
   else phisalpha_section<GRAD, EMIT>(b, dq, n, h, em, (size_t)2 * P * KF);
   for (int i = n - 2; i >= 0; --i) {
     BodyRegs bi, bj, bn;
@@ -250,7 +250,7 @@ __device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em,
     for (int j = n - 1; j >= i + 1; --j, ++rec) {
       bj = bn;
       if (j - 1 >= i + 1) load_body<GRAD>(b, dq, j - 1, bn);
-      if (!kicked(kmask, i * n - i * (i + 1) / 2 + (j - i - 1))) pair_section<GRAD, EMIT>(bi, bj, h2, false, em, (size_t)rec * KF);
+      if (!kicks || !kicked(kmask, i * n - i * (i + 1) / 2 + (j - i - 1))) pair_section<GRAD, EMIT>(bi, bj, h2, false, em, (size_t)rec * KF);
       store_body<GRAD>(b, dq, j, bj);
     }
     store_body<GRAD>(b, dq, i, bi);
@@ -262,7 +262,7 @@ __device__ void ahl21_step(Body& b, double* dq, int n, double h, const Emit& em,
       if (GRAD) dq[6 * i + k] += 0.5 * b.v[3 * i + k] + h2 * dq[6 * i + 3 + k];
     }
   }
-  if (kmask) kick_section<GRAD, EMIT>(b, dq, n, h / 6.0, kmask, false, em, phi_rec_offset(n, 2));
+  if (kicks) kick_section<GRAD, EMIT>(b, dq, n, h / 6.0, kmask, false, em, phi_rec_offset(n, 2));
 }
 
 // timing.jl:141-150  g!, gd!   (i = transited body, j = occultor)

@@ -23,6 +23,13 @@ namespace nbg {
 constexpr int NMAX = 16;  // max bodies per system
 constexpr int KF = 64;    // doubles per Kepler-pair operator record
 constexpr int PF = 24;    // doubles per phisalpha-pair operator record
+// Fast-kick pairs (s.pair): bit p = pair index i*n - i(i+1)/2 + (j-i-1), i < j; N <= 16 -> 120 pairs in 128 bits.
+struct KMask {
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  __host__ __device__ __forceinline__ bool any() const { return (w[0] | w[1] | w[2] | w[3]) != 0u; }
+  __host__ __device__ __forceinline__ bool bit(int p) const { return (w[(p >> 5) & 3] >> (p & 31)) & 1u; }
+  __host__ __device__ __forceinline__ void set(int p) { w[(p >> 5) & 3] |= 1u << (p & 31); }
+};
 constexpr int SCF = 12;   // doubles per pair section in the scalar stream of the split path: x0, v0, gamma, k, m_i, m_j (+2 pad); see kepler_scalars
 
 // Kepler record fields.  The 6x6 block jac_kepler is stored as four 3x3 blocks ordered for the Jacobian kernel's

@@ -369,16 +369,58 @@ def test_fast_kick_pairs_transit_timing(nb, oracle, elements):
     assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
 
 
-def test_errors_are_loud(nb, elements):
-    # fast-kick pairs are built for nbody <= 8 only: anything larger is refused, not silently ignored
-    n = 10
+def _wide_elements(n):
     el = np.zeros((n, 7)); el[0, 0] = 1.0
     for k in range(1, n):
-        el[k] = [3e-5, 1.5 * 1.6 ** (k - 1), 0.1 * k, 0.01, 0.0, np.pi / 2, 0.0]
-    s = nb.State(nb.ElementsIC(0.0, n, el))
-    s.pair[1, 2] = True
-    with pytest.raises(nb.NbgError):
-        nb.Integrator(0.05, 1.0)(s, 2)
+        el[k] = [1e-3 * (1 + 0.1 * k), 1.5 * 1.35 ** (k - 1), 0.1 * k, 0.01 * np.cos(k), 0.01 * np.sin(k), np.pi / 2 - 0.001 * k, 0.02 * k]
+    return el
+
+
+# one case per shared-memory regime of the fast-kick Jacobian kernel: two operator buffers (9, 11), one (12, 14), one + the first kick's
+# scratch in local memory (15, 16); pair indices beyond bit 31 / 63 / 95 of the 128-bit pair mask
+@pytest.mark.parametrize("n,kick", [(9, [(1, 2), (7, 8)]), (11, [(2, 3), (9, 10), (4, 10)]), (12, [(1, 2), (10, 11), (5, 9)]),
+                                    (14, [(3, 4), (12, 13), (0, 13)]), (15, [(1, 2), (13, 14), (6, 7)]),
+                                    (16, [(1, 2), (14, 15), (7, 11), (12, 15)])])
+def test_fast_kick_pairs_more_than_8_bodies(nb, oracle, n, kick):
+    # kickfast!/phic! work for any N in the reference (ahl21.jl:337-386, :392-552); r1 refused N > 8
+    el = _wide_elements(n)
+    x, v, _ = oracle.init_nbody(el, 0.0)
+    pair = np.zeros((n, n), dtype=bool)
+    for i, j in kick:
+        pair[i, j] = True
+    for h, nsteps, grad in ((0.05, 9, True), (-0.03, 4, True), (0.05, 9, False)):
+        so = oracle.new_state(x, v, el[:, 0], 0.0); so["pair"] = pair
+        oracle.integrate(so, h, nsteps=nsteps, grad=grad)
+        s = nb.State(cartesian_ic(nb, x, v, el[:, 0], 0.0)); s.pair[...] = pair
+        nb.Integrator(abs(h), 10.0)(s, nsteps if h > 0 else -nsteps, grad=grad)
+        assert rel(s.x[0], so["x"]) < TOL and rel(s.v[0], so["v"]) < TOL
+        if grad:
+            assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+            assert rel(s.dqdt[0], so["dqdt"]) < TOL
+    s0 = nb.State(cartesian_ic(nb, x, v, el[:, 0], 0.0))
+    nb.Integrator(0.05, 10.0)(s0, 9, grad=False)
+    assert rel(s0.x[0], so["x"]) > 1e-10   # not the default map
+
+
+@pytest.mark.parametrize("n", [10, 13])
+def test_fast_kick_pairs_transit_timing_more_than_8_bodies(nb, oracle, n):
+    t0, h, tmax = 0.0, 0.05, 6.0
+    el = _wide_elements(n)
+    pair = np.zeros((n, n), dtype=bool); pair[2, 3] = True; pair[n - 2, n - 1] = True
+    x, v, jac = oracle.init_nbody(el, t0)
+    so = oracle.new_state(x, v, el[:, 0], t0); so["pair"] = pair
+    ic = nb.ElementsIC(t0, n, el)
+    s, tt = nb.State(ic), nb.TransitTiming(tmax, ic)
+    s.pair[...] = pair
+    r = oracle.transit_timing(so, h, tmax, tt.ntt, grad=True, jac_init=jac)
+    nb.Integrator(h, tmax)(s, tt)
+    _cmp_tt(tt.tt[0], tt.count[0], r)
+    assert r["count"].sum() > 5
+    assert rel(tt.dtdq0[0], r["dtdq0"]) < TOL and rel(tt.dtdelements[0], r["dtdelements"]) < TOL
+    assert rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
+
+
+def test_errors_are_loud(nb, elements):
     import ctypes as C
     L = nb.lib()
     p = C.c_void_p()

@@ -19,7 +19,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 NBG_OVERLAP=0 timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 3 > gpurun_out/${R}_bench_serialized.json 2> gpurun_out/bench_ser.err
 timeout 300 python bench.py --no-cpu-baseline --steps 3 --e2e-input elements --e2e-output chi2 > gpurun_out/${R}_bench_elements_chi2.json 2> gpurun_out/bench_chi2.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch.log 2>&1
-cuobjdump -sass -fun "$(cuobjdump -elf $LIB 2>/dev/null | grep -o '_ZN[^ ]*jac_rx_kernelILi8ELi4ELb0ELi2ELb0ELb1E[^ ]*' | head -1)" $LIB 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4}\*/" | awk '{print $2}' | sed 's/;//' | sort | uniq -c | sort -rn | head -40 > gpurun_out/${R}_jac_rx_sass_mix.txt
+cuobjdump -sass -fun "$(cuobjdump -elf $LIB 2>/dev/null | grep -o '_ZN[^ ]*jac_rx_kernelILi8ELi4ELb0ELi2ELb0ELb1E[^ ]*' | head -1)" $LIB 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4,}\*/" | awk '{print $2}' | sed 's/;//' | sort | uniq -c | sort -rn | head -40 > gpurun_out/${R}_jac_rx_sass_mix.txt
 timeout 900 python bench.py --full --full-output chi2 > gpurun_out/${R}_bench_full_chi2_65536.json 2> gpurun_out/bench_full.err; echo "full rc=$?"
 tail -n 3 gpurun_out/smoke.log; tail -n 3 gpurun_out/bench.err; cat gpurun_out/${R}_bench.json; cat gpurun_out/${R}_bench_reference.json; cat gpurun_out/${R}_bench_full_chi2_65536.json
 python - <<'PY'
