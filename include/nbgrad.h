@@ -26,7 +26,7 @@
  *    used from different threads.  Calls block until results are in the host buffers.
  *  - s.pair (Integrator.jl:91; all-false by default, nothing in src/ sets it): `pair` is Julia's N x N Bool matrix
  *    (entry [i,j] at i + N*j, one byte each; only i < j is read, as in the reference) or NULL = all-false.  Flagged pairs
- *    get kickfast!/phic! instead of Kepler drifts (ahl21.jl:337-552); supported for nbody <= 8, else NBG_ERR_UNSUPPORTED.
+ *    get kickfast!/phic! instead of Kepler drifts (ahl21.jl:337-552); any nbody <= 16 (128-bit pair mask).
  *    One pair matrix applies to every system of the batch.
  *  - there is no CPU fallback: without a CUDA device every compute call returns NBG_ERR_NO_DEVICE.
  */
@@ -103,9 +103,13 @@ int32_t nbg_integrate_resident(nbg_plan* plan, double h, int64_t nsteps, double 
 
 /* (intr)(s, o::CartesianOutput) (src/outputs/Outputs.jl:26-49): nsteps steps of size h from the resident state (s.t = t0 + h i);
  * x, v BEFORE every `stride`-th step (Outputs.jl:40 saves the state before the step) are returned as
- * x_samples[k][sys][body][3], k = 0 .. ceil(nsteps/stride)-1.  The reference also keeps jac_step per saved State; here the
- * Jacobian is available at the end (nbg_get_state), or per sample by cutting the integration into calls. */
+ * x_samples[k][sys][body][3], k = 0 .. ceil(nsteps/stride)-1.
+ * The reference keeps the whole State per sample, jac_step included (Outputs.jl:40 deepcopy): nbg_integrate_sampled_jac also returns
+ * jac_samples[k][sys][7n x 7n, Julia column-major] = jac_step before step k*stride (k = 0: the identity); needs grad = 1; the chunks of the
+ * device pipeline then end on sample steps.  jac_samples = NULL: identical to nbg_integrate_sampled. */
 int32_t nbg_integrate_sampled(nbg_plan* plan, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples);
+int32_t nbg_integrate_sampled_jac(nbg_plan* plan, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples,
+                                  double* jac_samples);
 
 /* get_orbital_elements(s, ic) (src/outputs/elements.jl:108-137) of the resident state of every system, on the device:
  * elements_out[sys][body][11] = (m, P, t0 = 0, ecosw, esinw, I, Omega, a, e, omega, tp), the fields of the reference's Elements (body 0 carries

@@ -254,6 +254,33 @@ function chi2_fused(bi::B200Integrator, ss::Vector{State{Float64}}, tts::Vector{
     return chi2, g
 end
 
+# ---- (intr)(s, o::CartesianOutput)  src/outputs/Outputs.jl:26-49 --------------------------------------------------------
+# o.states[i] = deepcopy(s) before step i: positions, velocities and jac_step of every saved state come back from ONE call
+# (nbg_integrate_sampled_jac); the other fields of the copies (m, pair, n, ...) are those of the input state, t = t0 + h (i-1).
+function (bi::B200Integrator)(ss::Vector{State{Float64}}, os::Vector{CartesianOutput{Float64}})
+    B, n = length(ss), ss[1].n
+    length(os) == B || throw(ArgumentError("one CartesianOutput per system"))
+    nstep = os[1].nstep
+    all(o -> o.nstep == nstep, os) || throw(ArgumentError("the batch shares nstep"))
+    t0 = ss[1].t[1]
+    h = bi.h * NbodyGradient.check_step(t0, bi.tmax)
+    p = plan(n, B, bi.device)
+    upload(p, ss, true)
+    xs = zeros(Float64, 3, n, B, nstep); vs = zeros(Float64, 3, n, B, nstep); js = zeros(Float64, 7n, 7n, B, nstep)
+    chk(ccall((:nbg_integrate_sampled_jac, LIB), Int32, (Ptr{Cvoid}, Float64, Int64, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              p, h, nstep, 1, 1, xs, vs, js))
+    for (b, (s, o)) in enumerate(zip(ss, os)), i in 1:nstep
+        c = deepcopy(s)
+        c.x .= @view xs[:, :, b, i]; c.v .= @view vs[:, :, b, i]; c.jac_step .= @view js[:, :, b, i]
+        c.t[1] = t0 + h * (i - 1)
+        o.states[i] = c
+    end
+    download!(p, ss, true)
+    for s in ss; s.t[1] = t0 + h * nstep; end
+    return
+end
+(bi::B200Integrator)(s::State{Float64}, o::CartesianOutput{Float64}) = bi([s], [o])
+
 # single-system forms: a batch of one
 (bi::B200Integrator)(s::State{Float64}, tt::TransitOutput{Float64}; grad::Bool=true) = (bi([s], [tt]; grad=grad); nothing)
 (bi::B200Integrator)(s::State{Float64}, time::Float64; grad::Bool=true) = (bi([s], time; grad=grad); nothing)

@@ -8,9 +8,9 @@
 //   transit_kernel    one THREAD per queued transit: findtransit! Newton iterations (timing.jl:31-73), Jacobian-free because x, v,
 //                     dqdt never read jac_step; then the one final step (timing.jl:75-80) whose operator records are written
 //   jac_rx_kernel     one block per system, jac_step + jac_error in REGISTERS for the whole chunk (two lanes per column), operator
-//                     block of a step staged in shared memory; at each queued transit saves the matrix, applies the transit step,
-//                     emits dtbvdq! (timing.jl:155-194) or accumulates the fused chi^2 gradient, restores.  (N = 15, 16: jac_kernel,
-//                     matrix in shared memory.)
+//                     block of a step staged in shared memory; at each queued transit one dot product per column with the adjoint
+//                     vectors of the transit sub-step (transit_adjoint_kernel, nbg_adjoint.cuh) gives dtbvdq! (timing.jl:155-194) or
+//                     the fused chi^2 gradient.  All N = 2..16; with fast-kick pairs the KICK variant (three dense operators per step).
 // The host loop (run_steps) reads the number of queued transits back after the trajectory kernel of every chunk: a queue that is too
 // small is grown and the chunk re-run from a saved trajectory state (no transit is ever dropped), and the per-transit buffers are sized
 // from the actual count.  One-shot calls stream every chunk's transit rows to the caller's host arrays while the next chunk computes.
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(64) transit_adjoint_kernel(EventQueue Q, int n
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Jacobian kernel (generic N; used for N = 15, 16): one block per system, blockDim = 32*ceil(M/32) threads, thread c owns column c.
+// Jacobian kernel (generic N; only with NBG_FORCE_GENERIC_JAC=1 since r2): one block per system, blockDim = 32*ceil(M/32) threads, thread c owns column c.
 __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g, int n, size_t ld, const double* stream,
                            int nsteps, double h, const int32_t* evlist, EventQueue Q, int ti, TransitOut O, int stage_phi) {
   extern __shared__ double sm[];
@@ -388,7 +388,7 @@ __global__ void jac_kernel(double* __restrict__ Jv_g, double* __restrict__ Je_g,
   }
 }
 
-// Register-resident Jacobian kernel (N <= NBG_RX_MAX_BODIES = 14): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
+// Register-resident Jacobian kernel (N <= NBG_RX_MAX_BODIES = 16): one block per system, rx_warps(N) warps, see nbg_jacobian_rx.cuh.
 // register budget: 48 + 48 doubles of resident state (jac_step + jac_error halves) at N = 8 plus temporaries needs ~246 registers -> 2 blocks
 // of 4 warps per SM; N = 9: 2 blocks of 4 warps at 255 registers; N = 10: 2 blocks of 5 warps at 168 registers; N = 11..14: one block of 5-7
 // warps per SM (255 registers, 136-219 KB of operator ring)
@@ -1001,6 +1001,7 @@ struct nbg_plan {
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> tev;  // timing events, created once and reused by every call (Timer)
   bool has_state = false, jac_valid = false, force_generic_jac = false, split_traj = true, overlap = true, overlap3 = false;
+  double* samp_jac = nullptr;  // nbg_integrate_sampled_jac: jac_step before every samp_stride-th step, [sample][sys][7n][7n] (Julia layout); null = off
   KMask kmask;  // fast-kick pairs (s.pair), bit = pair index i*n - i(i+1)/2 + (j-i-1), i < j
   int rx_unroll = 38;
   int phi_cached = 2;  // NBG_PHI_CACHED: 0 = phi_dense_kernel without the shared-memory cache of the per-pair tensors, 1 = T / gam cached, 2 = all pair fields
@@ -1250,7 +1251,17 @@ int run_steps(nbg_plan* p, double h, long nsteps, bool grad, bool detect, int ti
   int prev_buf = -1;  // staging buffer whose device-to-host copy may still read the event-row buffers
   long done = 0;
   while (done < nsteps) {
-    const int s = (int)std::min<long>(S, nsteps - done);
+    int s = (int)std::min<long>(S, nsteps - done);
+    if (p->samp_jac && grad) {
+      // the saved State of the reference carries jac_step (Outputs.jl:40 deep-copies it): chunks end on sample steps, and the matrix of
+      // every sample step is copied out (in stream order, after the previous chunk's Jacobian kernel) before the chunk that starts there
+      const long st = p->T.samp_stride;
+      if (done % st == 0) {
+        jac_to_julia_kernel<<<(unsigned)nsys, 256, 0, p->stream>>>(p->bJv.as<double>(), p->samp_jac + (size_t)(done / st) * nsys * M * M, n, 0);
+        p->launches++;
+      }
+      s = (int)std::min<long>(s, st - done % st);
+    }
     double* tkerr = kahan_time ? p->bterr.as<double>() : nullptr;
     int s_split = 0;  // steps of this chunk whose Kepler records come from pair_op_kernel (split path)
     long nq = 0;
@@ -1912,17 +1923,20 @@ int32_t nbg_integrate_resident(nbg_plan* p, double h, int64_t nsteps, double h_l
 
 // (intr)(s, o::CartesianOutput) (Outputs.jl:26-49) without the per-step host round trip: positions and velocities before every
 // `stride`-th step are collected on the device and copied out once.
-int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples) {
+int32_t nbg_integrate_sampled_jac(nbg_plan* p, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples,
+                                  double* jac_samples) {
   if (!p) return fail(NBG_ERR_ARG, "plan is NULL");
   if (nsteps < 1 || stride < 1 || !x_samples || !v_samples) return fail(NBG_ERR_ARG, "nsteps >= 1, stride >= 1 and both sample buffers are required");
+  if (jac_samples && !grad) return fail(NBG_ERR_ARG, "jac_step samples need grad = true");
   if (!p->kids.empty()) {  // a slice's samples are [k][its systems]: collected per slice, then interleaved into [k][all systems]
-    const size_t n3 = 3 * (size_t)p->n, nsamp = (size_t)((nsteps + stride - 1) / stride), B = (size_t)p->nsys;
+    const size_t n3 = 3 * (size_t)p->n, MM = (size_t)49 * p->n * p->n, nsamp = (size_t)((nsteps + stride - 1) / stride), B = (size_t)p->nsys;
     return for_kids(p, [&](nbg_plan* k, long lo, long cnt) {
-      std::vector<double> xs(nsamp * cnt * n3), vs(nsamp * cnt * n3);
-      if (int r = nbg_integrate_sampled(k, h, nsteps, stride, grad, xs.data(), vs.data())) return r;
+      std::vector<double> xs(nsamp * cnt * n3), vs(nsamp * cnt * n3), js(jac_samples ? nsamp * cnt * MM : 0);
+      if (int r = nbg_integrate_sampled_jac(k, h, nsteps, stride, grad, xs.data(), vs.data(), jac_samples ? js.data() : nullptr)) return r;
       for (size_t q = 0; q < nsamp; ++q) {
         std::memcpy(x_samples + (q * B + lo) * n3, xs.data() + q * cnt * n3, cnt * n3 * 8);
         std::memcpy(v_samples + (q * B + lo) * n3, vs.data() + q * cnt * n3, cnt * n3 * 8);
+        if (jac_samples) std::memcpy(jac_samples + (q * B + lo) * MM, js.data() + q * cnt * MM, cnt * MM * 8);
       }
       return 0;
     });
@@ -1930,26 +1944,29 @@ int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t str
   if (!p->has_state) return fail(NBG_ERR_ARG, "no state set");
   CK(cudaSetDevice(p->device));
   p->generation++;
-  const size_t n = p->n, nsys = p->nsys, ld = p->ld;
+  const size_t n = p->n, nsys = p->nsys, ld = p->ld, MM = 49 * n * n;
   const long nsamp = (long)((nsteps + stride - 1) / stride);
-  DevBuf sx, sv, ox;
-  if (sx.ensure((size_t)nsamp * 3 * n * ld * 8) || sv.ensure((size_t)nsamp * 3 * n * ld * 8) || ox.ensure((size_t)nsamp * 3 * n * nsys * 8)) {
-    sx.release(); sv.release(); ox.release();
+  DevBuf sx, sv, ox, sj;
+  auto release = [&]() { sx.release(); sv.release(); ox.release(); sj.release(); };
+  if (sx.ensure((size_t)nsamp * 3 * n * ld * 8) || sv.ensure((size_t)nsamp * 3 * n * ld * 8) || ox.ensure((size_t)nsamp * 3 * n * nsys * 8) ||
+      (jac_samples && sj.ensure((size_t)nsamp * nsys * MM * 8))) {
+    release();
     return fail(NBG_ERR_NOMEM, "sample buffers do not fit (reduce nsteps / stride or the batch)");
   }
   double t0 = 0;
   CK(cudaMemcpy(&t0, p->bt.p, 8, cudaMemcpyDeviceToHost));
-  if (grad) if (int r = make_jac_identity(p)) { sx.release(); sv.release(); ox.release(); return r; }
+  if (grad) if (int r = make_jac_identity(p)) { release(); return r; }
   p->T.samp_x = sx.as<double>(); p->T.samp_v = sv.as<double>(); p->T.samp_stride = (long)stride;
+  p->samp_jac = jac_samples ? sj.as<double>() : nullptr;
   Timer tm(p);
   tm.start();
   // s.t[1] = t0 + h i (Outputs.jl:43): same time bookkeeping as the transit driver
   const int rc = run_steps(p, h, (long)nsteps, grad != 0, false, 0, t0, h, false, tm, 0.0);
-  p->T.samp_x = nullptr; p->T.samp_v = nullptr;
+  p->T.samp_x = nullptr; p->T.samp_v = nullptr; p->samp_jac = nullptr;
   tm.stop();
   cudaStreamSynchronize(p->stream);
   finish_timings(p, tm);
-  if (rc) { sx.release(); sv.release(); ox.release(); return rc; }
+  if (rc) { release(); return rc; }
   const dim3 grid((unsigned)((nsys + 127) / 128), (unsigned)nsamp);
   double* outs[2] = {x_samples, v_samples};
   const double* srcs[2] = {sx.as<double>(), sv.as<double>()};
@@ -1959,10 +1976,17 @@ int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t str
     cudaMemcpyAsync(outs[q], ox.p, (size_t)nsamp * 3 * n * nsys * 8, cudaMemcpyDeviceToHost, p->stream);
     cudaStreamSynchronize(p->stream);
   }
+  if (jac_samples) {
+    cudaMemcpyAsync(jac_samples, sj.p, (size_t)nsamp * nsys * MM * 8, cudaMemcpyDeviceToHost, p->stream);
+    cudaStreamSynchronize(p->stream);
+  }
   const cudaError_t err = cudaGetLastError();
-  sx.release(); sv.release(); ox.release();
+  release();
   if (err != cudaSuccess) return fail(NBG_ERR_CUDA, cudaGetErrorString(err));
   return NBG_OK;
+}
+int32_t nbg_integrate_sampled(nbg_plan* p, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples) {
+  return nbg_integrate_sampled_jac(p, h, nsteps, stride, grad, x_samples, v_samples, nullptr);
 }
 
 // get_orbital_elements(s, ic) (src/outputs/elements.jl:108-137) for the resident state of every system: the adjacent step after the path

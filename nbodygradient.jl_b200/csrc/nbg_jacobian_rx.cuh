@@ -1,4 +1,4 @@
-// Register-resident Jacobian propagation for N <= NBG_RX_MAX_BODIES = 14 bodies (the production path; nbg_jacobian.cuh is the generic
+// Register-resident Jacobian propagation for N <= NBG_RX_MAX_BODIES = 16 bodies (the production path; nbg_jacobian.cuh is the generic
 // shared-memory version used for N = 15, 16, where 12 N doubles of resident state per thread no longer fit in 255 registers
 // and a double-buffered operator block no longer fits in 227 KB of shared memory).
 //

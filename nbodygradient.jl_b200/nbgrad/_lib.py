@@ -11,7 +11,7 @@ ST_NONFINITE, ST_TRANSIT_ITMAX, ST_EVENT_OVERFLOW, ST_NTT_OVERFLOW = 1, 2, 4, 8
 
 # every symbol include/nbgrad.h declares
 SYMBOLS = ["nbg_version", "nbg_last_error", "nbg_device_count", "nbg_plan_create", "nbg_plan_destroy", "nbg_set_pair", "nbg_set_state", "nbg_set_state_elements", "nbg_get_jac_init", "nbg_get_state",
-           "nbg_integrate_resident", "nbg_integrate_sampled", "nbg_integrate", "nbg_transit_timing_resident", "nbg_transit_fetch", "nbg_transit_chi2", "nbg_transit_timing",
+           "nbg_integrate_resident", "nbg_integrate_sampled", "nbg_integrate_sampled_jac", "nbg_integrate", "nbg_transit_timing_resident", "nbg_transit_fetch", "nbg_transit_chi2", "nbg_transit_timing",
            "nbg_counters", "nbg_counters_reset", "nbg_last_timings", "nbg_cuda_stream", "nbg_fp64_peak", "nbg_build_flags", "nbg_plan_create_multi", "nbg_plan_devices",
            "nbg_state_generation", "nbg_transit_chi2_fused", "nbg_chunk_retries", "nbg_orbital_elements", "nbg_source_hash"]
 

@@ -253,11 +253,12 @@ class ElementsOutput:
 
 class CartesianOutput:
     """CartesianOutput(nbody, nstep) -- Outputs.jl:7-17.  The reference deep-copies the whole State before every step; here x and v
-    before every `stride`-th step are collected on the device (nbg_integrate_sampled): o.x[k, b, i, :], o.v[k, b, i, :], o.t[k]."""
+    before every `stride`-th step are collected on the device (nbg_integrate_sampled): o.x[k, b, i, :], o.v[k, b, i, :], o.t[k].
+    jac=True (needs grad=True) also keeps the saved States' jac_step: o.jac_step[k, b, :, :] (row, column as State.jac_step)."""
 
-    def __init__(self, nbody, nstep, stride=1):
-        self.nbody, self.nstep, self.stride = int(nbody), int(nstep), int(stride)
-        self.x = self.v = self.t = None
+    def __init__(self, nbody, nstep, stride=1, jac=False):
+        self.nbody, self.nstep, self.stride, self.jac = int(nbody), int(nstep), int(stride), bool(jac)
+        self.x = self.v = self.t = self.jac_step = None
 
 
 class Integrator:
@@ -340,8 +341,16 @@ class Integrator:
         s._upload(plan, grad)
         o.x, o.v = np.zeros((ns, s.nsys, s.n, 3)), np.zeros((ns, s.nsys, s.n, 3))
         o.t = t0 + h * o.stride * np.arange(ns)
-        check(_lib.lib().nbg_integrate_sampled(plan, C.c_double(h), C.c_int64(o.nstep), C.c_int64(o.stride), C.c_int32(1 if grad else 0),
-                                               ptr(o.x), ptr(o.v)))
+        if o.jac:
+            if not grad:
+                raise _lib.NbgError("NBG_ERR_ARG: CartesianOutput(jac=True) needs grad=True")
+            M = 7 * s.n
+            jcm = np.zeros((ns, s.nsys, M, M))   # per system column-major (Julia layout)
+            check(_lib.lib().nbg_integrate_sampled_jac(plan, C.c_double(h), C.c_int64(o.nstep), C.c_int64(o.stride), C.c_int32(1), ptr(o.x), ptr(o.v), ptr(jcm)))
+            o.jac_step = np.ascontiguousarray(jcm.transpose(0, 1, 3, 2))
+        else:
+            check(_lib.lib().nbg_integrate_sampled(plan, C.c_double(h), C.c_int64(o.nstep), C.c_int64(o.stride), C.c_int32(1 if grad else 0),
+                                                   ptr(o.x), ptr(o.v)))
         s._download(plan, grad)
         self._timings(plan)
 

@@ -372,7 +372,8 @@ def test_fast_kick_pairs_transit_timing(nb, oracle, elements):
 def _wide_elements(n):
     el = np.zeros((n, 7)); el[0, 0] = 1.0
     for k in range(1, n):
-        el[k] = [1e-3 * (1 + 0.1 * k), 1.5 * 1.35 ** (k - 1), 0.1 * k, 0.01 * np.cos(k), 0.01 * np.sin(k), np.pi / 2 - 0.001 * k, 0.02 * k]
+        # (Jupiter-mass planets at period ratio 1.35 make this ill-conditioned: the oracle's own jac_step moves by 7e-11 under 1-ulp changes of x, v)
+        el[k] = [1e-4 * (1 + 0.1 * k), 1.5 * 1.45 ** (k - 1), 0.1 * k, 0.01 * np.cos(k), 0.01 * np.sin(k), np.pi / 2 - 0.001 * k, 0.02 * k]
     return el
 
 
@@ -1010,6 +1011,33 @@ def test_cartesian_output_sampling(nb, oracle, elements):
     oracle.integrate(so, h, nsteps=nstep - done, grad=True)
     assert rel(s.x[0], so["x"]) < TOL and rel(s.jac_step[0], so["jac_step_cm"].T) < TOL
     assert abs(s.t[0] - (t0 + h * nstep)) < 1e-9
+
+
+@pytest.mark.parametrize("n,devices", [(4, None), (8, [0, 0])])
+def test_cartesian_output_keeps_jac_step(nb, oracle, elements, n, devices):
+    # Outputs.jl:40 deep-copies the whole State, jac_step included, before every step: CartesianOutput(jac=True) returns the matrix of every
+    # saved state (nbg_integrate_sampled_jac; chunks of the device pipeline end on sample steps).  Against the oracle stepped to the same
+    # instants; the final state must be bit-identical to the same integration without samples (chunk cuts do not change jac_step).
+    t0, h, nstep, stride, B = 7257.0, 0.05, 43, 5, 3
+    elb = _perturbed_trappist(elements[:n], B, 21)
+    ic = nb.ElementsIC(t0, n, elb)
+    s, o = nb.State(ic), nb.CartesianOutput(n, nstep, stride, jac=True)
+    kw = {"devices": devices} if devices else {}
+    nb.Integrator(h, t0 + 1000.0, **kw)(s, o)
+    ns = (nstep + stride - 1) // stride
+    assert o.jac_step.shape == (ns, B, 7 * n, 7 * n)
+    assert np.array_equal(o.jac_step[0], np.broadcast_to(np.eye(7 * n), (B, 7 * n, 7 * n)))
+    for b in range(B):
+        x, v, _ = oracle.init_nbody(elb[b], t0)
+        so = oracle.new_state(x, v, elb[b, :, 0], t0)
+        for k in range(1, ns):
+            oracle.integrate(so, h, nsteps=stride, grad=True)
+            assert rel(o.x[k, b], so["x"]) < TOL and rel(o.jac_step[k, b], so["jac_step_cm"].T) < TOL
+    s2 = nb.State(ic)
+    nb.Integrator(h, t0 + 1000.0)(s2, nstep)
+    assert np.array_equal(s.jac_step, s2.jac_step) and np.array_equal(s.x, s2.x) and np.array_equal(s.dqdt, s2.dqdt)
+    with pytest.raises(nb.NbgError):
+        nb.Integrator(h, t0 + 1000.0)(nb.State(ic), nb.CartesianOutput(n, nstep, stride, jac=True), grad=False)
 
 
 def test_orbital_elements_output(nb, oracle, elements):
