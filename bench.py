@@ -150,6 +150,11 @@ def cpu_run(nsys, window, nthreads, x, v, m, jac_init):
     return nsys * window / dt, dt, r
 
 
+def workload_name(ngpus):
+    """the same string in both arms (own and --impl reference)"""
+    return "TRAPPIST-1 N=8 h=0.06 grad=true TransitTiming (BASELINE cfg %s)" % ("2" if ngpus == 1 else "5 shard: 131,072 systems per GPU = 1,048,576 on 8")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,7 +175,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "system-steps/s w/ grad (TRAPPIST-1 batch)", "value": value, "unit": "system-steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "TRAPPIST-1 N=8 h=0.06 grad=true TransitTiming (cfg 2)", "batch": 65536, "sample_batch": nsys, "window_steps": window},
+           "config": {"workload": workload_name(args.gpus), "batch_per_gpu": args.nsys if args.nsys > 0 else (65536 if args.gpus == 1 else 131072),
+                      "sample_batch": nsys, "window_steps": window,
+                      "parallelism": "CPU: one system per host thread, %d threads" % cores},
            "cpu_baseline": {"value": value, "unit": "system-steps/s", "cores": cores, "kind": "port",
                             "sample": "%d systems x %d steps per step, oracle -O3 build, one system per thread" % (nsys, window)},
            "e2e": {"value": value, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -544,7 +551,7 @@ def main():
         "metric": "system-steps/s w/ grad (TRAPPIST-1 batch)", "value": value, "unit": "system-steps/s", "n_gpus": world * ngpu, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "TRAPPIST-1 N=8 h=0.06 grad=true TransitTiming (BASELINE cfg %s)" % ("2" if world * ngpu == 1 else "5 shard: 131,072 systems per GPU = 1,048,576 on 8"),
+        "config": {"workload": workload_name(world * ngpu),
                    "batch_per_gpu": args.nsys, "window_steps": window,
                    "chunk_steps": int(cnt[6]), "jac_launches": int(cnt[7]),
                    "l2": "inputs larger than L2: operator stream %.1f GB + scalar stream %.1f GB per chunk, jac_step %.1f GB per GPU (L2 = 126 MB)" %
