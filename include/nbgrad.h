@@ -105,7 +105,8 @@ int32_t nbg_integrate_resident(nbg_plan* plan, double h, int64_t nsteps, double 
  * x, v BEFORE every `stride`-th step (Outputs.jl:40 saves the state before the step) are returned as
  * x_samples[k][sys][body][3], k = 0 .. ceil(nsteps/stride)-1.
  * The reference keeps the whole State per sample, jac_step included (Outputs.jl:40 deepcopy): nbg_integrate_sampled_jac also returns
- * jac_samples[k][sys][7n x 7n, Julia column-major] = jac_step before step k*stride (k = 0: the identity); needs grad = 1; the chunks of the
+ * jac_samples[k][sys][7n x 7n, Julia column-major] = jac_step before step k*stride (k = 0: the resident jac_step, i.e. the identity for a
+ * fresh State -- the reference does not reset it either); needs grad = 1; the chunks of the
  * device pipeline then end on sample steps.  jac_samples = NULL: identical to nbg_integrate_sampled. */
 int32_t nbg_integrate_sampled(nbg_plan* plan, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples);
 int32_t nbg_integrate_sampled_jac(nbg_plan* plan, double h, int64_t nsteps, int64_t stride, int32_t grad, double* x_samples, double* v_samples,
