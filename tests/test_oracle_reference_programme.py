@@ -168,6 +168,26 @@ def test_flagged_pairs_above_8_bodies_vs_float128_fd(oracle, n, kick):
     assert isapprox_maxabs(s0["jac_step_cm"].T, jac0_num)
 
 
+def test_cartesian_to_elements_round_trip(oracle, elements):
+    # test/test_cartesian_to_elements.jl:14-38: ElementsIC(t0, [4,1,1,1], "elements.txt") -> State -> get_orbital_elements gives the input
+    # elements back, tolerance 1e-10 on every field but a, e, varpi.  (The reference's loop compares elems[1] with system[1] four times;
+    # here all four bodies are compared.)  Pins the oracle's restatement of src/outputs/elements.jl:108-137, which the device kernel
+    # (nbg_orbital_elements) is tested against.
+    t0 = 7257.93115525 - 7300.0
+    el = elements[:4].copy()
+    x, v, _ = oracle.init_nbody(el, t0)
+    out = oracle.orbital_elements(x, v, el[:, 0])
+    assert np.max(np.abs(out[:, 0] - el[:, 0])) < 1e-10                        # m
+    assert np.max(np.abs(out[1:, 1] - el[1:, 1])) < 1e-10                      # P
+    assert np.max(np.abs(out[1:, 3:7] - el[1:, 3:7])) < 1e-10                  # ecosw, esinw, I, Omega
+    assert np.all(out[0, 1:] == 0.0)                                            # the first body carries only its mass
+    # a, e, omega, tp are consistent with the rest: Kepler's third law and e = |(ecosw, esinw)|
+    G = 39.4845 / (365.242 * 365.242)                                          # GNEWT, src/NbodyGradient.jl
+    msum = np.cumsum(el[:, 0])
+    assert np.max(np.abs(out[1:, 7] ** 3 / (G * msum[1:]) * 4 * np.pi ** 2 - out[1:, 1] ** 2) / out[1:, 1] ** 2) < 1e-10
+    assert np.max(np.abs(out[1:, 8] - np.hypot(el[1:, 3], el[1:, 4]))) < 1e-10
+
+
 def _tt_setup(elements):
     N = 3
     t0 = T0 - 7300.0 - 0.5
