@@ -57,3 +57,24 @@ def test_two_rank_gloo_shard_reduce_gather(nsys):
         assert ms == 15.0                                  # max over ranks, identical on every rank
         assert tot == [float(nsys), float(expect.sum())]   # every system counted exactly once
         assert np.array_equal(np.array(full), expect)      # gather restores the global order
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    # the driver launches `bench.py --impl reference` like the GPU arm (torchrun for N > 1): rank 0 alone times the CPU oracle and
+    # prints ONE JSON line with the contract's keys, the other ranks exit 0 without work.  No GPU involved.
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29631",
+           os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--ref-window", "16",
+           "--ref-systems-per-core", "1"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "system-steps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "cfg 5" in d["config"]["workload"] and d["config"]["batch_per_gpu"] == 131072
