@@ -133,6 +133,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+CPU_BUILD = "oracle -O3 build"
+
+
 def cpu_run(nsys, window, nthreads, x, v, m, jac_init):
     """Reference CPU path (oracle, -O3 build) on `nsys` systems for `window` steps, one system per thread."""
     from oracle.binding import Oracle, build
@@ -140,7 +143,9 @@ def cpu_run(nsys, window, nthreads, x, v, m, jac_init):
         build(fast_native=True)  # rebuild the timing build for this host's ISA
     except Exception:
         pass
-    o = Oracle(fast=True)
+    o = Oracle(fast=True, blas=not os.environ.get("NBG_REF_NO_BLAS"))
+    global CPU_BUILD
+    CPU_BUILD = "oracle -O3 build, " + ("dense products (the reference's mul! calls) through %s" % o.blas if o.blas else "built-in loop nests for the dense products (no OpenBLAS found)")
     tmax = window * H
     ntt = int(np.ceil(tmax / 1.5) + 3)
     jcm = np.ascontiguousarray(jac_init[:nsys].transpose(0, 2, 1))
@@ -179,7 +184,7 @@ def run_reference(args):
                       "sample_batch": nsys, "window_steps": window,
                       "parallelism": "CPU: one system per host thread, %d threads" % cores},
            "cpu_baseline": {"value": value, "unit": "system-steps/s", "cores": cores, "kind": "port",
-                            "sample": "%d systems x %d steps per step, oracle -O3 build, one system per thread" % (nsys, window)},
+                            "sample": "%d systems x %d steps per step, %s, one system per thread" % (nsys, window, CPU_BUILD)},
            "e2e": {"value": value, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -577,7 +582,7 @@ def main():
         ns = cores * args.ref_systems_per_core
         rate, dt, r = cpu_run(ns, args.ref_window, cores, x, v, m, jac_init)
         out["cpu_baseline"] = {"value": rate, "unit": "system-steps/s", "cores": cores, "kind": "port",
-                               "sample": "%d systems x %d steps (%.1f s), oracle -O3 build, one system per thread" % (ns, args.ref_window, dt)}
+                               "sample": "%d systems x %d steps (%.1f s), %s, one system per thread" % (ns, args.ref_window, dt, CPU_BUILD)}
         if e2e_tt is not None and args.e2e_input == "cartesian":
             # the CPU sample ran the first `ns` systems of this batch from the same state: their transits inside the bench window are the
             # same events the end-to-end arm returned -- compare them (the oracle as the checker of the timed arm)

@@ -27,8 +27,34 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def find_openblas():
+    """(CDLL, dgemm symbol name, description) of an LP64 OpenBLAS that ships with the Python stack (scipy's), or None.
+    The reference's mul! calls are OpenBLAS dgemm (Julia LinearAlgebra); the CPU-baseline timing build can use the same."""
+    import glob
+    try:
+        import scipy
+    except Exception:
+        return None
+    root = os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs")
+    for path in sorted(glob.glob(os.path.join(root, "libscipy_openblas*.so"))):
+        if "64_" in os.path.basename(path):
+            continue   # ILP64 build: 64-bit integer arguments
+        try:
+            lib = C.CDLL(path)
+            fn = getattr(lib, "scipy_dgemm_")
+            try:
+                lib.scipy_openblas_set_num_threads(C.c_int(1))   # the batch is threaded over systems
+            except AttributeError:
+                pass
+            return lib, fn, "OpenBLAS dgemm (%s, 1 thread per call)" % os.path.basename(path)
+        except (OSError, AttributeError):
+            continue
+    return None
+
+
 class Oracle:
-    def __init__(self, fast=False):
+    def __init__(self, fast=False, blas=False):
+        """fast: the -O3 timing build.  blas (timing build only): dense products through OpenBLAS dgemm, as the reference's mul! calls."""
         name = "libnbg_oracle_fast.so" if fast else "libnbg_oracle.so"
         path = os.path.join(_HERE, name)
         if not os.path.exists(path):
@@ -36,6 +62,16 @@ class Oracle:
         self.lib = C.CDLL(path)
         self.lib.nbgo_gnewt.restype = C.c_double
         self.GNEWT = self.lib.nbgo_gnewt()
+        self.blas = None
+        if blas:
+            if not fast:
+                raise ValueError("BLAS products are for the timing build only: the reference-semantics build keeps the k-ascending loops")
+            found = find_openblas()
+            if found is not None:
+                self._blas_lib, fn, self.blas = found
+                self.lib.nbgo_set_dgemm(C.cast(fn, C.c_void_p))
+        elif fast and hasattr(self.lib, "nbgo_set_dgemm"):
+            self.lib.nbgo_set_dgemm(None)
 
     # ---- IC layer ---------------------------------------------------------
     def init_nbody(self, elements, t0, eps=None):

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <type_traits>
 #include <quadmath.h>
 
 namespace nbgo {
@@ -282,7 +283,20 @@ template <class T> inline bool all_zero(const T* A, size_t len) {
   for (size_t q = 0; q < len; ++q) if (A[q] != T(0)) return false;
   return true;
 }
+// CPU-BASELINE TIMING ONLY: the reference's mul! calls go to OpenBLAS (Julia's LinearAlgebra), so the timing build of this oracle can be
+// handed a Fortran-interface dgemm (nbgo_set_dgemm; bench.py passes the OpenBLAS that ships with scipy, single-threaded: the batch is
+// threaded over systems).  Never set in the reference-semantics build that the parity tests use (BLAS kernels round differently).
+using dgemm_fn = void (*)(const char*, const char*, const int*, const int*, const int*, const double*, const double*, const int*, const double*,
+                          const int*, const double*, double*, const int*);
+inline dgemm_fn& blas_dgemm() { static dgemm_fn f = nullptr; return f; }
 template <class T> inline void gemm(T* C, const T* A, const T* B, int ma, int ka, int nb) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (blas_dgemm() && !skip_zero_gemm()) {
+      const double one = 1.0, zero = 0.0;
+      blas_dgemm()("N", "N", &ma, &nb, &ka, &one, A, &ma, B, &ka, &zero, C, &ma);
+      return;
+    }
+  }
   for (size_t q = 0; q < (size_t)ma * nb; ++q) C[q] = T(0);
   if (skip_zero_gemm() && all_zero(A, (size_t)ma * ka)) return;
   for (int c = 0; c < nb; ++c) {

@@ -55,6 +55,9 @@ int nbgo_version() { return 1; }
 // stale operator (quirk B-2, ahl21.jl:712-716); affects the calling thread only
 int nbgo_set_b2_identity(int on) { b2_identity() = on != 0; return 0; }
 double nbgo_gnewt() { return GNEWT; }
+// CPU-baseline timing only: route the dense products (the reference's mul! calls) through a Fortran-interface dgemm; NULL = the built-in loops
+int nbgo_set_dgemm(void* f) { blas_dgemm() = (dgemm_fn)f; return 0; }
+int nbgo_has_dgemm() { return blas_dgemm() != nullptr; }
 
 // ElementsIC(t0, H, elements) -> State(ic): x, v, jac_init.   elements is n x 7 column-major.
 int nbgo_init_nbody(int n, const double* elements, double t0, const double* eps, double* x, double* v, double* jac_init) {
