@@ -145,7 +145,7 @@ def cpu_run(nsys, window, nthreads, x, v, m, jac_init):
         pass
     o = Oracle(fast=True, blas=not os.environ.get("NBG_REF_NO_BLAS"))
     global CPU_BUILD
-    CPU_BUILD = "oracle -O3 build, " + ("dense products (the reference's mul! calls) through %s" % o.blas if o.blas else "built-in loop nests for the dense products (no OpenBLAS found)")
+    CPU_BUILD = "oracle -O3 build, " + ("dense products (the reference's mul! calls) through %s" % o.blas if o.blas else "built-in loop nests for the dense products (%s)" % ("NBG_REF_NO_BLAS set" if os.environ.get("NBG_REF_NO_BLAS") else "no OpenBLAS found"))
     tmax = window * H
     ntt = int(np.ceil(tmax / 1.5) + 3)
     jcm = np.ascontiguousarray(jac_init[:nsys].transpose(0, 2, 1))
