@@ -143,9 +143,9 @@ def cpu_run(nsys, window, nthreads, x, v, m, jac_init):
         build(fast_native=True)  # rebuild the timing build for this host's ISA
     except Exception:
         pass
-    o = Oracle(fast=True, blas=not os.environ.get("NBG_REF_NO_BLAS"))
+    o = Oracle(fast=True, blas=not os.environ.get("NBGRAD_REF_NO_BLAS"))
     global CPU_BUILD
-    CPU_BUILD = "oracle -O3 build, " + ("dense products (the reference's mul! calls) through %s" % o.blas if o.blas else "built-in loop nests for the dense products (%s)" % ("NBG_REF_NO_BLAS set" if os.environ.get("NBG_REF_NO_BLAS") else "no OpenBLAS found"))
+    CPU_BUILD = "oracle -O3 build, " + ("dense products (the reference's mul! calls) through %s" % o.blas if o.blas else "built-in loop nests for the dense products (%s)" % ("NBGRAD_REF_NO_BLAS set" if os.environ.get("NBGRAD_REF_NO_BLAS") else "no OpenBLAS found"))
     tmax = window * H
     ntt = int(np.ceil(tmax / 1.5) + 3)
     jcm = np.ascontiguousarray(jac_init[:nsys].transpose(0, 2, 1))

@@ -6,7 +6,7 @@ make -C oracle -s
 nproc; lscpu | grep "Model name"
 for i in 1 2; do
   timeout 100 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02z_ref_blas_$i.json
-  NBG_REF_NO_BLAS=1 timeout 100 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02z_ref_loops_$i.json
+  NBGRAD_REF_NO_BLAS=1 timeout 100 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02z_ref_loops_$i.json
 done
 python - <<'PY'
 import json
