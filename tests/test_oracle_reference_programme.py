@@ -315,3 +315,27 @@ def test_cfg2_full_length_oracle_vs_quad_golden(oracle, elements):
              "dtdq0": rel(pick(r["dtdq0"]), g["dtdq0_rows"]), "dtdelements": rel(pick(r["dtdelements"]), g["dtdelements_rows"])}
     print("Float64 round-off floor of the reference algorithm at 26,667 steps (relative max-norm vs __float128):", floor)
     assert floor["x"] < 1e-10 and floor["v"] < 1e-10 and floor["jac_step"] < 1e-8 and floor["dtdq0"] < 1e-8 and floor["dtdelements"] < 1e-8
+
+
+def test_timing_build_with_openblas_computes_the_same_thing(elements):
+    # bench.py's CPU arm routes the dense products of the oracle's -O3 build through OpenBLAS dgemm (the reference's mul! calls are OpenBLAS
+    # too).  Same algorithm, other summation order inside the products: transit times and gradients must agree with the loop-nest build
+    # far below the parity tolerance, otherwise the baseline would be timing something else.
+    from oracle.binding import Oracle, find_openblas
+    if find_openblas() is None:
+        pytest.skip("no LP64 OpenBLAS next to scipy")
+    n, t0, h, tmax = 8, 7257.0, 0.06, 20.0
+    el = elements[:n]
+    res = []
+    for blas in (False, True):
+        o = Oracle(fast=True, blas=blas)
+        assert (o.blas is not None) == blas
+        x, v, jac = o.init_nbody(el, t0)
+        s = o.new_state(x, v, el[:, 0], t0)
+        res.append((o.transit_timing(s, h, tmax, 16, grad=True, jac_init=jac), s))
+    (ra, sa), (rb, sb) = res
+    assert np.array_equal(ra["count"], rb["count"]) and ra["count"].sum() > 20
+    rel = lambda a, b: np.max(np.abs(a - b)) / np.max(np.abs(b))
+    assert rel(ra["tt"], rb["tt"]) < 1e-14 and rel(ra["dtdq0"], rb["dtdq0"]) < 1e-12 and rel(ra["dtdelements"], rb["dtdelements"]) < 1e-12
+    assert rel(sa["jac_step_cm"], sb["jac_step_cm"]) < 1e-12
+    Oracle(fast=True)   # leaves the timing build on its loop nests
